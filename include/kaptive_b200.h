@@ -1,0 +1,153 @@
+/* kaptive_b200.h -- C-ABI of libkaptive_b200.so
+ *
+ * Drop-in boundary for the one hot path of klebgenomics/Kaptive that this
+ * library replaces: mapping every K/O-locus reference gene onto the contigs of
+ * draft assemblies.  In the reference that path is the `rammappy` module
+ * (third-party Rust wheel), reached through exactly these call sites:
+ *
+ *   rammappy.fasta.parse_fasta_bytes   src/kaptive/core/genome.py:45
+ *   rammappy.Index.build               src/kaptive/core/genome.py:188-189
+ *   rammappy.align.Aligner(...)        src/kaptive/serotyping/core.py:148-152
+ *   Aligner.map_batch(gene_seqs)       src/kaptive/serotyping/core.py:154
+ *   hit fields drained per record      src/kaptive/core/alignment.py:409-446
+ *
+ * Each entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; no exceptions cross the ABI; every function
+ * returns 0 on success or a negative kb_status, and kb_last_error() gives the
+ * thread-local message.  Handles are immutable after creation and may be
+ * shared between threads; each mapping call uses its own CUDA stream.
+ *
+ * There is NO CPU fallback: without a CUDA device (or without the library)
+ * every compute entry point fails with KB_ERR_CUDA.
+ */
+#ifndef KAPTIVE_B200_H
+#define KAPTIVE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    KB_OK = 0,
+    KB_ERR_ARG = -1,       /* bad argument */
+    KB_ERR_CUDA = -2,      /* CUDA runtime failure / no device */
+    KB_ERR_LIMIT = -3,     /* input exceeds a documented limit */
+    KB_ERR_CAPACITY = -4,  /* caller buffer too small */
+    KB_ERR_INTERNAL = -5
+} kb_status;
+
+/* Mapping parameters: minimap2 defaults with no preset (what
+ * Aligner(preset=None) means, serotyping/core.py:148) plus the two overrides
+ * the reference applies (best_n=50000, pri_ratio=0.0, core.py:150-151), which
+ * together mean "keep and extend every chain". */
+typedef struct kb_params {
+    int32_t k, w;
+    int32_t min_cnt, min_chain_score, bw, max_gap, max_chain_skip, max_chain_iter;
+    float chain_gap_scale;
+    int32_t a, b, q, e, q2, e2, sc_ambi;
+    int32_t zdrop, min_dp_max, min_ksw_len;
+    int32_t mid_occ;            /* <=0: derived per assembly as minimap2 does */
+    int32_t min_mid_occ, max_mid_occ;
+    float mid_occ_frac, q_occ_frac, mask_level;
+    int32_t mask_len;
+    int32_t seed;
+    int32_t ext_bw;
+    int32_t max_sw_cells;
+} kb_params_t;
+
+void kb_params_default(kb_params_t *p);
+
+const char *kb_last_error(void);
+int kb_version(void);
+/* number of CUDA devices visible to the library (0 => nothing can run) */
+int kb_device_count(void);
+
+/* ---- FASTA ingest: replaces rammappy.fasta.parse_fasta_bytes (genome.py:45) ----
+ * Two-phase: count records, then fill caller arrays.  name_off/name_len and
+ * seq_off/seq_len index into `data`; sequences that span several lines are
+ * compacted IN a caller-provided output buffer `seq_out` (>= n bytes). */
+int kb_fasta_count(const uint8_t *data, int64_t n, int64_t *n_records, int64_t *n_seq_bytes);
+int kb_fasta_parse(const uint8_t *data, int64_t n, int64_t max_records,
+                   int64_t *name_off, int32_t *name_len,
+                   uint8_t *seq_out, int64_t seq_cap, int64_t *seq_off, int32_t *seq_len);
+
+/* ---- gene index: the query side of map_batch (serotyping/core.py:111-121,154) ----
+ * Built once per database; device-resident hash of every gene minimizer. */
+typedef struct kb_index kb_index_t;
+int kb_index_create(const uint8_t *gene_seqs, const int64_t *offsets, const int32_t *lengths,
+                    int32_t n_genes, const kb_params_t *params, int device, kb_index_t **out);
+void kb_index_destroy(kb_index_t *idx);
+int32_t kb_index_n_genes(const kb_index_t *idx);
+int64_t kb_index_n_minimizers(const kb_index_t *idx);
+/* flat byte image for a one-off NCCL/MPI broadcast to other ranks */
+int64_t kb_index_serialized_size(const kb_index_t *idx);
+int kb_index_serialize(const kb_index_t *idx, uint8_t *buf, int64_t cap);
+int kb_index_deserialize(const uint8_t *buf, int64_t n, int device, kb_index_t **out);
+
+/* ---- assembly batch: replaces rammappy.Index.build (genome.py:188-189) ----
+ * Contigs of n_asm assemblies, concatenated ASCII.  `contig_seqs` may be a
+ * host pointer (pageable or pinned) or a device pointer (UVA).  The batch
+ * keeps only the 2-bit packed sequence + ambiguity mask in HBM. */
+typedef struct kb_batch kb_batch_t;
+int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
+                    const int32_t *asm_contig_start /* n_asm+1 */, int32_t n_asm, int device, kb_batch_t **out);
+void kb_batch_destroy(kb_batch_t *b);
+int32_t kb_batch_n_assemblies(const kb_batch_t *b);
+int64_t kb_batch_total_bases(const kb_batch_t *b);
+int64_t kb_batch_packed_bytes(const kb_batch_t *b);
+
+/* ---- mapping: replaces Aligner(...).map_batch(gene_seqs) (serotyping/core.py:148-154) ---- */
+typedef struct kb_result kb_result_t;
+
+/* One field per array, Alignments-style SoA (core/alignment.py:295-317). */
+typedef struct kb_hits {
+    int64_t capacity;
+    int32_t *asm_id;        /* assembly index within the batch */
+    int32_t *gene;          /* query index == int(q_name) (serotyping/core.py:158) */
+    int32_t *q_start, *q_end;
+    int32_t *t_ctg;         /* contig index within its assembly (-> target_name) */
+    int32_t *t_len, *t_start, *t_end;
+    int8_t  *strand;        /* +1 / -1 */
+    int32_t *score, *matches, *block_len, *edit_distance;
+    uint8_t *mapq;
+    uint8_t *is_primary;
+    int64_t *cigar_off;     /* into the cigar pool */
+    int32_t *n_cigar;
+} kb_hits_t;
+
+int kb_map_batch(const kb_index_t *idx, const kb_batch_t *batch, kb_result_t **out);
+int kb_result_size(const kb_result_t *r, int64_t *n_hits, int64_t *n_cigar);
+/* copy device results into caller (host) arrays; hits ordered by (asm, gene, rank) */
+int kb_result_fetch(const kb_result_t *r, kb_hits_t *dst, uint32_t *cigar, int64_t cigar_cap);
+void kb_result_destroy(kb_result_t *r);
+
+/* per-stage device time of the call that produced `r`, CUDA events on its stream */
+enum { KB_STAGE_SCAN = 0, KB_STAGE_SORT, KB_STAGE_CHAIN, KB_STAGE_ALIGN, KB_STAGE_FINAL, KB_STAGE_TOTAL, KB_N_STAGES };
+int kb_result_stage_ms(const kb_result_t *r, float *ms /* KB_N_STAGES */);
+/* counters: [0] minimizers scanned-out, [1] anchors, [2] query groups, [3] chains, [4] raw hits, [5] kernel launches, [6] DP cells */
+int kb_result_counters(const kb_result_t *r, int64_t *c /* 8 */);
+/* stage dumps for parity tests (device -> host); arrays of int32 records */
+int kb_result_fetch_anchors(const kb_result_t *r, int32_t *out /* n x 7: asm,gene,rev,rid,tpos,qpos,flags */, int64_t cap, int64_t *n);
+int kb_result_fetch_chains(const kb_result_t *r, int32_t *out /* n x 10: asm,gene,score,cnt,rev,rid,rs,re,qs,qe */, int64_t cap, int64_t *n);
+int kb_result_mid_occ(const kb_result_t *r, int32_t *out /* n_asm */);
+
+/* one-call convenience for HOST buffers (the end-to-end path): batch_create +
+ * map + fetch + destroy; copies are inside. */
+int kb_map_assemblies(const kb_index_t *idx,
+                      const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
+                      const int32_t *asm_contig_start, int32_t n_asm,
+                      kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cigar);
+
+/* ---- minimizer scan only (the roofline kernel), for benchmarking / parity ----
+ * Runs the scan kernel over the batch and returns all minimizers of assembly
+ * `asm_id` as (hash, contig, pos<<1|strand) triples, unsorted. */
+int kb_scan_minimizers(const kb_index_t *idx, const kb_batch_t *batch, int32_t asm_id,
+                       uint32_t *hash, int32_t *ctg, uint32_t *pos_strand, int64_t cap, int64_t *n);
+/* times `iters` launches of the seeding scan kernel alone; returns mean ms */
+int kb_bench_scan(const kb_index_t *idx, const kb_batch_t *batch, int iters, float *mean_ms, int64_t *n_anchors);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAPTIVE_B200_H */

@@ -1,0 +1,13 @@
+// kb_kernels.h -- launch prototypes shared between the .cu translation units.
+#pragma once
+#include "kb_common.cuh"
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+
+// counters: [0] minimizers, [1] anchors, [2] groups, [3] chains, [4] raw hits, [5] cigar words, [6] error bits, [7] debug dump count
+#define KB_N_COUNTERS 16
+
+void kb_launch_scan(const KbIndexView &ix, const KbBatchView &bt, uint64_t *akey, uint32_t *aval,
+                    unsigned long long *counters, int64_t anchor_cap, uint32_t *mz_hash, int32_t *mz_ctg,
+                    uint32_t *mz_pos, int64_t mz_cap, int32_t mz_asm, int n_sm, cudaStream_t st);
+#endif
