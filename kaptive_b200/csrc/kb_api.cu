@@ -1,0 +1,854 @@
+// kb_api.cu -- the C-ABI of libkaptive_b200.so (include/kaptive_b200.h) and the host-side
+// orchestration of one mapping call: scan -> sort -> groups -> occurrence filter (+ census
+// where needed) -> chain -> align -> finalise -> SoA.  Every call runs on its own CUDA
+// stream; stage times come from CUDA events recorded on that stream.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "kb_final.cuh"
+#include "kb_host.h"
+#include "kb_kernels.h"
+
+// ---- prototypes of the launchers in kb_pipeline.cu
+void kb_launch_pack(const uint8_t *, int64_t, const int64_t *, const int64_t *, const int32_t *, int32_t, int32_t, int64_t, int64_t,
+                    uint32_t *, uint32_t *, cudaStream_t);
+void kb_launch_occ(const uint64_t *, const uint32_t *, int64_t, int64_t, uint32_t *, int32_t, int32_t *, cudaStream_t);
+void kb_launch_group_flag(const uint64_t *, int64_t, uint8_t *, cudaStream_t);
+size_t kb_sort_pairs_temp_bytes(int64_t);
+cudaError_t kb_sort_pairs(void *, size_t, const uint64_t *, uint64_t *, const uint32_t *, uint32_t *, int64_t, int, cudaStream_t);
+size_t kb_sort_keys32_temp_bytes(int64_t);
+cudaError_t kb_sort_keys32(void *, size_t, const uint32_t *, uint32_t *, int64_t, int, cudaStream_t);
+size_t kb_select_temp_bytes(int64_t);
+cudaError_t kb_select_flagged(void *, size_t, const uint8_t *, int64_t *, int64_t *, int64_t, cudaStream_t);
+size_t kb_scan_temp_bytes(int64_t);
+cudaError_t kb_exclusive_sum(void *, size_t, const int32_t *, int64_t *, int64_t, cudaStream_t);
+size_t kb_rle_temp_bytes(int64_t);
+cudaError_t kb_rle(void *, size_t, const uint32_t *, uint32_t *, uint32_t *, int64_t *, int64_t, cudaStream_t);
+void kb_launch_chain(const KbIndexView &, const KbBatchView &, const uint64_t *, const uint32_t *, const int64_t *, int64_t, int64_t,
+                     const uint16_t *, const int32_t *, const KbChainWork &, uint64_t *, uint64_t *, KbGroupInfo *, KbChainRec *,
+                     unsigned long long *, int64_t, cudaStream_t);
+void kb_launch_align(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
+                     uint64_t *, uint8_t *, size_t, int, KbRawHit *, int64_t, uint32_t *, int64_t, unsigned long long *,
+                     unsigned long long *, cudaStream_t);
+void kb_launch_rawkey(const KbRawHit *, int64_t, uint64_t *, uint32_t *, cudaStream_t);
+void kb_launch_gather_raw(const KbRawHit *, const uint32_t *, int64_t, KbRawHit *, cudaStream_t);
+void kb_launch_finalize(const kb_params_t &, KbRawHit *, int64_t, const KbGroupInfo *, int32_t *, uint64_t *, int32_t *, cudaStream_t);
+void kb_launch_scatter(const KbRawHit *, const int32_t *, const int64_t *, int64_t, const KbGroupInfo *, const KbBatchView &,
+                       const kb_hits_t &, cudaStream_t);
+void kb_launch_group_nseed(const KbGroupInfo *, int64_t, int32_t *, cudaStream_t);
+void kb_launch_dump_anchors(const KbBatchView &, const KbGroupInfo *, int64_t, const int64_t *, const uint32_t *, const int32_t *,
+                            const int64_t *, int32_t *, cudaStream_t);
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) {                                                                      \
+            char b_[512];                                                                             \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw std::string(b_);                                                                    \
+        }                                                                                             \
+    } while (0)
+
+struct DevPool {  // frees everything it handed out, in reverse order, on the owning stream
+    cudaStream_t st = nullptr;
+    std::vector<void *> ptrs;
+    template <class T>
+    T *get(size_t n)
+    {
+        void *p = nullptr;
+        size_t bytes = n * sizeof(T);
+        if (bytes == 0) bytes = 16;
+        CU(cudaMallocAsync(&p, bytes, st));
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    void release(void *p)
+    {
+        for (size_t i = 0; i < ptrs.size(); ++i)
+            if (ptrs[i] == p) {
+                cudaFreeAsync(p, st);
+                ptrs.erase(ptrs.begin() + (long)i);
+                return;
+            }
+    }
+    void clear()
+    {
+        for (size_t i = ptrs.size(); i-- > 0;) cudaFreeAsync(ptrs[i], st);
+        ptrs.clear();
+    }
+    ~DevPool() { clear(); }
+};
+
+struct kb_index {
+    KbHostIndex host;
+    int device = 0;
+    uint8_t *d_blob = nullptr;
+    KbIndexView view;
+};
+
+struct kb_batch {
+    KbHostBatchLayout L;
+    int device = 0;
+    int n_sm = 148;
+    uint8_t *d_blob = nullptr;  // layout arrays
+    uint32_t *seq2 = nullptr, *nmask = nullptr;
+    KbBatchView view;
+    int64_t last_anchor_count = 0;  // sizing hint for repeated calls on the same batch
+};
+
+struct kb_result {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    int64_t n_hits = 0, n_cigar = 0;
+    kb_hits_t d;  // device SoA
+    uint32_t *pool = nullptr;
+    std::vector<void *> owned;
+    float stage_ms[KB_N_STAGES] = {0};
+    int64_t counters[8] = {0};
+    std::vector<int32_t> mid_occ;
+    // stage dumps
+    int32_t *d_anchor_dump = nullptr;
+    int64_t n_anchor_dump = 0;
+    std::vector<int32_t> chain_dump;
+};
+
+static void setup_mempool(int device)
+{
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+}
+
+template <class T>
+static size_t put_blob(std::vector<uint8_t> &blob, const std::vector<T> &v)
+{
+    size_t off = (blob.size() + 255) & ~(size_t)255;
+    blob.resize(off + v.size() * sizeof(T) + 16);
+    if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+}
+
+static int index_upload(kb_index *ix, int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KB_ERR_CUDA, "no CUDA device: libkaptive_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(KB_ERR_ARG, "bad device ordinal");
+    try {
+        CU(cudaSetDevice(device));
+        setup_mempool(device);
+        const KbHostIndex &h = ix->host;
+        std::vector<uint8_t> blob;
+        size_t o_ht = put_blob(blob, h.ht), o_ent = put_blob(blob, h.ent), o_gl = put_blob(blob, h.gene_len);
+        size_t o_gn = put_blob(blob, h.gene_nmin), o_gmo = put_blob(blob, h.gene_min_off), o_gq = put_blob(blob, h.gm_qpos_z);
+        size_t o_go = put_blob(blob, h.gm_qocc), o_gh = put_blob(blob, h.gene_hash), o_gso = put_blob(blob, h.gene_seq_off);
+        size_t o_f = put_blob(blob, h.gseq_fwd), o_r = put_blob(blob, h.gseq_rev);
+        CU(cudaMalloc((void **)&ix->d_blob, blob.size()));
+        CU(cudaMemcpy(ix->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        KbIndexView &v = ix->view;
+        v.p = h.p, v.n_genes = h.n_genes, v.n_entries = (int64_t)h.ent.size(), v.ht_mask = (uint32_t)h.ht.size() - 1;
+        uint8_t *b = ix->d_blob;
+        v.ht = (const uint64_t *)(b + o_ht), v.ent = (const KbEntry *)(b + o_ent), v.gene_len = (const int32_t *)(b + o_gl);
+        v.gene_nmin = (const int32_t *)(b + o_gn), v.gene_min_off = (const int64_t *)(b + o_gmo), v.gm_qpos_z = (const uint32_t *)(b + o_gq);
+        v.gm_qocc = (const int32_t *)(b + o_go), v.gene_hash = (const uint32_t *)(b + o_gh), v.gene_seq_off = (const int64_t *)(b + o_gso);
+        v.gseq_fwd = b + o_f, v.gseq_rev = b + o_r;
+        ix->device = device;
+    } catch (const std::string &e) {
+        return fail(KB_ERR_CUDA, e);
+    }
+    return KB_OK;
+}
+
+extern "C" {
+
+const char *kb_last_error(void) { return g_err.c_str(); }
+int kb_version(void) { return 100; }
+int kb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int kb_index_create(const uint8_t *gene_seqs, const int64_t *offsets, const int32_t *lengths, int32_t n_genes, const kb_params_t *params,
+                    int device, kb_index_t **out)
+{
+    if (!out || !params || (n_genes > 0 && (!gene_seqs || !offsets || !lengths))) return fail(KB_ERR_ARG, "null argument");
+    if (params->max_gap >= KB_CTG_VGAP - 64 || params->bw >= KB_CTG_VGAP - 64) return fail(KB_ERR_LIMIT, "max_gap/bw must stay below 8128");
+    if (params->max_sw_cells <= 0 || params->max_sw_cells > 64000000) return fail(KB_ERR_LIMIT, "max_sw_cells out of range");
+    kb_index *ix = new kb_index();
+    std::string err = ix->host.build(gene_seqs, offsets, lengths, n_genes, *params);
+    if (!err.empty()) {
+        delete ix;
+        return fail(KB_ERR_LIMIT, err);
+    }
+    int rc = index_upload(ix, device);
+    if (rc) {
+        delete ix;
+        return rc;
+    }
+    *out = ix;
+    return KB_OK;
+}
+
+void kb_index_destroy(kb_index_t *ix)
+{
+    if (!ix) return;
+    if (ix->d_blob) {
+        cudaSetDevice(ix->device);
+        cudaFree(ix->d_blob);
+    }
+    delete ix;
+}
+int32_t kb_index_n_genes(const kb_index_t *ix) { return ix ? ix->host.n_genes : 0; }
+int64_t kb_index_n_minimizers(const kb_index_t *ix) { return ix ? (int64_t)ix->host.ent.size() : 0; }
+int64_t kb_index_serialized_size(const kb_index_t *ix) { return ix ? ix->host.serialized_size() : 0; }
+int kb_index_serialize(const kb_index_t *ix, uint8_t *buf, int64_t cap)
+{
+    if (!ix || !buf) return fail(KB_ERR_ARG, "null argument");
+    if (cap < ix->host.serialized_size()) return fail(KB_ERR_CAPACITY, "buffer smaller than kb_index_serialized_size()");
+    ix->host.serialize(buf);
+    return KB_OK;
+}
+int kb_index_deserialize(const uint8_t *buf, int64_t n, int device, kb_index_t **out)
+{
+    if (!buf || !out) return fail(KB_ERR_ARG, "null argument");
+    kb_index *ix = new kb_index();
+    std::string err = ix->host.deserialize(buf, n);
+    if (!err.empty()) {
+        delete ix;
+        return fail(KB_ERR_ARG, err);
+    }
+    int rc = index_upload(ix, device);
+    if (rc) {
+        delete ix;
+        return rc;
+    }
+    *out = ix;
+    return KB_OK;
+}
+
+int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len, const int32_t *asm_contig_start,
+                    int32_t n_asm, int device, kb_batch_t **out)
+{
+    if (!out || !asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KB_ERR_CUDA, "no CUDA device: libkaptive_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(KB_ERR_ARG, "bad device ordinal");
+    kb_batch *b = new kb_batch();
+    std::string err = b->L.build(contig_off, contig_len, asm_contig_start, n_asm);
+    if (!err.empty()) {
+        delete b;
+        return fail(KB_ERR_LIMIT, err);
+    }
+    cudaStream_t st = nullptr;
+    uint8_t *d_ascii = nullptr;
+    try {
+        CU(cudaSetDevice(device));
+        setup_mempool(device);
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        b->n_sm = prop.multiProcessorCount;
+        b->device = device;
+        const KbHostBatchLayout &L = b->L;
+        std::vector<int64_t> off_v(contig_off, contig_off + L.n_ctg);
+        std::vector<uint8_t> blob;
+        size_t o_so = put_blob(blob, L.ctg_soff), o_len = put_blob(blob, L.ctg_len), o_asm = put_blob(blob, L.ctg_asm);
+        size_t o_vs = put_blob(blob, L.ctg_vstart), o_acs = put_blob(blob, L.asm_ctg_start), o_cc = put_blob(blob, L.chunk_ctg);
+        size_t o_cs = put_blob(blob, L.chunk_start), o_off = put_blob(blob, off_v);
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU(cudaMalloc((void **)&b->d_blob, blob.size()));
+        CU(cudaMemcpyAsync(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMalloc((void **)&b->seq2, (size_t)(L.storage_bases >> 4) * 4 + 64));
+        CU(cudaMalloc((void **)&b->nmask, (size_t)(L.storage_bases >> 5) * 4 + 64));
+        // lead-in / tail padding groups
+        CU(cudaMemsetAsync(b->seq2, 0, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
+        CU(cudaMemsetAsync(b->nmask, 0xff, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
+        uint8_t *db = b->d_blob;
+        KbBatchView &v = b->view;
+        v.n_asm = L.n_asm, v.n_ctg = L.n_ctg, v.n_chunks = (int64_t)L.chunk_ctg.size(), v.total_bases = L.total_bases;
+        v.seq2 = b->seq2, v.nmask = b->nmask;
+        v.ctg_soff = (const int64_t *)(db + o_so), v.ctg_len = (const int32_t *)(db + o_len), v.ctg_asm = (const int32_t *)(db + o_asm);
+        v.ctg_vstart = (const int32_t *)(db + o_vs), v.asm_ctg_start = (const int32_t *)(db + o_acs);
+        v.chunk_ctg = (const int32_t *)(db + o_cc), v.chunk_start = (const int32_t *)(db + o_cs);
+        const int64_t *d_off = (const int64_t *)(db + o_off);
+        // pack in slabs of <= 1 GiB of ASCII so the transient staging buffer stays bounded
+        const int64_t slab = (int64_t)1 << 30;
+        int c0 = 0;
+        int64_t staged_cap = 0;
+        while (c0 < L.n_ctg) {
+            int64_t lo = contig_off[c0], hi = lo;
+            int c1 = c0;
+            while (c1 < L.n_ctg) {
+                int64_t a = contig_off[c1], e = a + L.ctg_len[c1];
+                int64_t nlo = a < lo ? a : lo, nhi = e > hi ? e : hi;
+                if (c1 > c0 && nhi - nlo > slab) break;
+                lo = nlo, hi = nhi, ++c1;
+            }
+            int64_t bytes = hi - lo;
+            if (bytes > staged_cap) {
+                if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
+                staged_cap = bytes + 64;
+                CU(cudaMallocAsync((void **)&d_ascii, (size_t)staged_cap, st));
+            }
+            if (bytes > 0) CU(cudaMemcpyAsync(d_ascii, contig_seqs + lo, (size_t)bytes, cudaMemcpyDefault, st));
+            int64_t g0 = L.ctg_soff[c0] >> 5;
+            int64_t g1 = (c1 < L.n_ctg ? L.ctg_soff[c1] : L.storage_bases - 64) >> 5;
+            kb_launch_pack(d_ascii, lo, d_off, v.ctg_soff, v.ctg_len, c0, c1, g0, g1, b->seq2, b->nmask, st);
+            CU(cudaGetLastError());
+            c0 = c1;
+        }
+        if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
+        d_ascii = nullptr;
+        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamDestroy(st));
+    } catch (const std::string &e) {
+        if (st) cudaStreamDestroy(st);
+        if (b->d_blob) cudaFree(b->d_blob);
+        if (b->seq2) cudaFree(b->seq2);
+        if (b->nmask) cudaFree(b->nmask);
+        delete b;
+        return fail(KB_ERR_CUDA, e);
+    }
+    *out = b;
+    return KB_OK;
+}
+
+void kb_batch_destroy(kb_batch_t *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->d_blob) cudaFree(b->d_blob);
+    if (b->seq2) cudaFree(b->seq2);
+    if (b->nmask) cudaFree(b->nmask);
+    delete b;
+}
+int32_t kb_batch_n_assemblies(const kb_batch_t *b) { return b ? b->L.n_asm : 0; }
+int64_t kb_batch_total_bases(const kb_batch_t *b) { return b ? b->L.total_bases : 0; }
+int64_t kb_batch_packed_bytes(const kb_batch_t *b) { return b ? (b->L.storage_bases >> 2) + (b->L.storage_bases >> 3) : 0; }
+
+void kb_result_destroy(kb_result_t *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    for (void *p : r->owned) cudaFree(p);
+    delete r;
+}
+
+}  // extern "C"
+
+// minimap2 mm_idx_cal_max_occ for one assembly, on the device: dump its minimizer hashes with the
+// scan kernel, radix sort, run-length encode, sort the run lengths, read the quantile.
+static int32_t census_one(const kb_index *ix, const kb_batch *bt, int asm_id, DevPool &P, unsigned long long *d_counters, cudaStream_t st)
+{
+    const kb_params_t &p = ix->host.p;
+    const KbHostBatchLayout &L = bt->L;
+    int64_t bases = 0;
+    for (int c = L.asm_ctg_start[asm_id]; c < L.asm_ctg_start[asm_id + 1]; ++c) bases += L.ctg_len[c];
+    int64_t cap = bases / 2 + 4 * (int64_t)(L.asm_ctg_start[asm_id + 1] - L.asm_ctg_start[asm_id]) + 1024;
+    uint32_t *h = P.get<uint32_t>((size_t)cap), *h2 = P.get<uint32_t>((size_t)cap), *pos = P.get<uint32_t>((size_t)cap);
+    int32_t *ctg = P.get<int32_t>((size_t)cap);
+    uint32_t *cnt = P.get<uint32_t>((size_t)cap), *cnt2 = P.get<uint32_t>((size_t)cap);
+    int64_t *d_n = P.get<int64_t>(1);
+    CU(cudaMemsetAsync(d_counters + 16, 0, 16 * 8, st));
+    // restrict the scan to this assembly's chunks
+    KbBatchView v = bt->view;
+    int64_t k0 = 0, k1 = 0;
+    {
+        const std::vector<int32_t> &cc = L.chunk_ctg;
+        int lo_c = L.asm_ctg_start[asm_id], hi_c = L.asm_ctg_start[asm_id + 1];
+        k0 = std::lower_bound(cc.begin(), cc.end(), lo_c) - cc.begin();
+        k1 = std::lower_bound(cc.begin(), cc.end(), hi_c) - cc.begin();
+    }
+    v.chunk_ctg += k0, v.chunk_start += k0, v.n_chunks = k1 - k0;
+    kb_launch_scan(ix->view, v, nullptr, nullptr, d_counters + 16, 0, h, ctg, pos, cap, asm_id, bt->n_sm, st);
+    CU(cudaGetLastError());
+    unsigned long long n_mz = 0;
+    CU(cudaMemcpyAsync(&n_mz, d_counters + 23, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((int64_t)n_mz > cap) throw std::string("census buffer overflow");
+    int32_t mid;
+    if (n_mz == 0) mid = INT32_MAX;
+    else {
+        size_t tb = kb_sort_keys32_temp_bytes((int64_t)n_mz), tb2 = kb_rle_temp_bytes((int64_t)n_mz);
+        if (tb2 > tb) tb = tb2;
+        uint8_t *tmp = P.get<uint8_t>(tb);
+        CU(kb_sort_keys32(tmp, tb, h, h2, (int64_t)n_mz, 30, st));
+        CU(kb_rle(tmp, tb, h2, h, cnt, d_n, (int64_t)n_mz, st));
+        int64_t n_runs = 0;
+        CU(cudaMemcpyAsync(&n_runs, d_n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(kb_sort_keys32(tmp, tb, cnt, cnt2, n_runs, 32, st));
+        uint32_t kth = (uint32_t)((1. - p.mid_occ_frac) * (double)n_runs), val = 0;
+        CU(cudaMemcpyAsync(&val, cnt2 + kth, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        mid = (int32_t)(val + 1);
+        P.release(tmp);
+    }
+    if (mid < p.min_mid_occ) mid = p.min_mid_occ;
+    if (p.max_mid_occ > p.min_mid_occ && mid > p.max_mid_occ) mid = p.max_mid_occ;
+    P.release(h), P.release(h2), P.release(pos), P.release(ctg), P.release(cnt), P.release(cnt2), P.release(d_n);
+    return mid;
+}
+
+static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, bool keep_stages)
+{
+    if (ix->device != bt->device) return fail(KB_ERR_ARG, "index and batch live on different devices");
+    const kb_params_t &p = ix->host.p;
+    kb_result *R = new kb_result();
+    R->device = ix->device;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[KB_N_STAGES + 1];
+    for (auto &e : ev) e = nullptr;
+    DevPool P;
+    int launches = 0;
+    try {
+        CU(cudaSetDevice(ix->device));
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        P.st = st;
+        for (auto &e : ev) CU(cudaEventCreate(&e));
+        const KbBatchView &bv = bt->view;
+        const KbIndexView &iv = ix->view;
+        const int n_asm = bv.n_asm;
+        unsigned long long *d_counters = P.get<unsigned long long>(KB_N_COUNTERS);
+        unsigned long long hc[KB_N_COUNTERS];
+
+        // ---------------- scan (+ rerun once if the anchor buffer was too small)
+        int64_t anchor_cap = bt->last_anchor_count > 0 ? bt->last_anchor_count + bt->last_anchor_count / 16 + 1024 : bv.total_bases / 48 + (1 << 20);
+        uint64_t *akey = nullptr;
+        uint32_t *aval = nullptr;
+        int64_t n_anchors = 0;
+        CU(cudaEventRecord(ev[0], st));
+        for (int attempt = 0;; ++attempt) {
+            akey = P.get<uint64_t>((size_t)anchor_cap), aval = P.get<uint32_t>((size_t)anchor_cap);
+            CU(cudaMemsetAsync(d_counters, 0, KB_N_COUNTERS * 8, st));
+            kb_launch_scan(iv, bv, akey, aval, d_counters, anchor_cap, nullptr, nullptr, nullptr, 0, -1, bt->n_sm, st);
+            ++launches;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            n_anchors = (int64_t)hc[1];
+            if (hc[6] & 1) throw std::string("scan queue overflow (internal limit)");
+            if (n_anchors <= anchor_cap) break;
+            if (attempt >= 2) throw std::string("anchor buffer overflow");
+            P.release(akey), P.release(aval);
+            anchor_cap = n_anchors + n_anchors / 16 + 1024;
+        }
+        bt->last_anchor_count = n_anchors;
+        if (n_anchors >= ((int64_t)1 << 31)) throw std::string("more than 2^31 anchors in one batch: split the batch");
+        CU(cudaEventRecord(ev[1], st));
+        R->counters[0] = (int64_t)hc[0], R->counters[1] = n_anchors;
+
+        // ---------------- occurrence counts, census where needed
+        std::vector<int32_t> mid_occ((size_t)n_asm, p.mid_occ > 0 ? p.mid_occ : p.min_mid_occ);
+        size_t occ_words = ((size_t)n_asm * (size_t)iv.n_entries + 1) / 2 + 4;
+        uint32_t *occ32 = P.get<uint32_t>(occ_words);
+        int32_t *d_need = P.get<int32_t>((size_t)n_asm + 1);
+        CU(cudaMemsetAsync(occ32, 0, occ_words * 4, st));
+        CU(cudaMemsetAsync(d_need, 0, ((size_t)n_asm + 1) * 4, st));
+        kb_launch_occ(akey, aval, n_anchors, iv.n_entries, occ32, p.min_mid_occ, d_need, st);
+        ++launches;
+        CU(cudaGetLastError());
+        {
+            std::vector<int32_t> need((size_t)n_asm + 1, 0);
+            CU(cudaMemcpyAsync(need.data(), d_need, (size_t)n_asm * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const char *fc = getenv("KAPTIVE_B200_FORCE_CENSUS");
+            bool force = (fc && fc[0] == '1') || ix->host.max_qocc > p.min_mid_occ;
+            for (int a = 0; a < n_asm; ++a) {
+                if (need[(size_t)a] == 2) throw std::string("a gene minimizer occurs more than 65519 times in one assembly (limit)");
+                if (p.mid_occ <= 0 && (need[(size_t)a] || force)) {
+                    mid_occ[(size_t)a] = census_one(ix, bt, a, P, d_counters, st);
+                    launches += 4;
+                }
+            }
+        }
+        int32_t *d_mid = P.get<int32_t>((size_t)n_asm + 1);
+        CU(cudaMemcpyAsync(d_mid, mid_occ.data(), (size_t)n_asm * 4, cudaMemcpyHostToDevice, st));
+        R->mid_occ = mid_occ;
+
+        // ---------------- sort anchors by (asm, gene, strand, position)
+        uint64_t *skey = P.get<uint64_t>((size_t)n_anchors + 1);
+        uint32_t *sval = P.get<uint32_t>((size_t)n_anchors + 1);
+        {
+            size_t tb = kb_sort_pairs_temp_bytes(n_anchors);
+            uint8_t *tmp = P.get<uint8_t>(tb);
+            if (n_anchors > 0) CU(kb_sort_pairs(tmp, tb, akey, skey, aval, sval, n_anchors, 60, st));
+            launches += 8;
+            P.release(tmp);
+        }
+        P.release(akey), P.release(aval);
+        // groups
+        uint8_t *gflag = P.get<uint8_t>((size_t)n_anchors + 1);
+        int64_t *gstart = P.get<int64_t>((size_t)n_anchors + 1);
+        int64_t *d_ng = P.get<int64_t>(1);
+        int64_t n_groups = 0;
+        if (n_anchors > 0) {
+            kb_launch_group_flag(skey, n_anchors, gflag, st);
+            size_t tb = kb_select_temp_bytes(n_anchors);
+            uint8_t *tmp = P.get<uint8_t>(tb);
+            CU(kb_select_flagged(tmp, tb, gflag, gstart, d_ng, n_anchors, st));
+            launches += 3;
+            CU(cudaMemcpyAsync(&n_groups, d_ng, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            P.release(tmp);
+        }
+        P.release(gflag);
+        CU(cudaEventRecord(ev[2], st));
+        R->counters[2] = n_groups;
+
+        // ---------------- chaining
+        KbChainWork W;
+        W.x = P.get<uint32_t>((size_t)n_anchors + 1), W.y = P.get<int32_t>((size_t)n_anchors + 1);
+        W.f = P.get<int32_t>((size_t)n_anchors + 1), W.p = P.get<int32_t>((size_t)n_anchors + 1);
+        W.v = P.get<int32_t>((size_t)n_anchors + 1), W.t = P.get<int32_t>((size_t)n_anchors + 1);
+        W.z = P.get<uint64_t>((size_t)n_anchors + 1), W.u = P.get<uint64_t>((size_t)n_anchors + 1);
+        uint64_t *cx = P.get<uint64_t>((size_t)n_anchors + 1), *cy = P.get<uint64_t>((size_t)n_anchors + 1);
+        KbGroupInfo *ginfo = P.get<KbGroupInfo>((size_t)n_groups + 1);
+        int64_t chain_cap = n_anchors / 3 + 16;
+        KbChainRec *chains = P.get<KbChainRec>((size_t)chain_cap);
+        kb_launch_chain(iv, bv, skey, sval, gstart, n_groups, n_anchors, (const uint16_t *)occ32, d_mid, W, cx, cy, ginfo, chains,
+                        d_counters, chain_cap, st);
+        ++launches;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int64_t n_chains = (int64_t)hc[3];
+        if (n_chains > chain_cap) throw std::string("chain buffer overflow");
+        CU(cudaEventRecord(ev[3], st));
+        R->counters[3] = n_chains;
+        if (keep_stages && n_groups > 0) {  // anchors after the occurrence filters, chains before alignment
+            int32_t *nseed = P.get<int32_t>((size_t)n_groups + 1);
+            int64_t *aoff = P.get<int64_t>((size_t)n_groups + 1);
+            kb_launch_group_nseed(ginfo, n_groups, nseed, st);
+            size_t tb = kb_scan_temp_bytes(n_groups);
+            uint8_t *tmp = P.get<uint8_t>(tb);
+            CU(kb_exclusive_sum(tmp, tb, nseed, aoff, n_groups, st));
+            int64_t last_off = 0;
+            int32_t last_n = 0;
+            CU(cudaMemcpyAsync(&last_off, aoff + n_groups - 1, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(&last_n, nseed + n_groups - 1, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            R->n_anchor_dump = last_off + last_n;
+            CU(cudaMalloc((void **)&R->d_anchor_dump, (size_t)(R->n_anchor_dump + 1) * 7 * 4));
+            R->owned.push_back(R->d_anchor_dump);
+            kb_launch_dump_anchors(bv, ginfo, n_groups, gstart, W.x, W.y, aoff, R->d_anchor_dump, st);
+            std::vector<KbChainRec> hch((size_t)n_chains);
+            std::vector<KbGroupInfo> hg((size_t)n_groups);
+            CU(cudaMemcpyAsync(hch.data(), chains, (size_t)n_chains * sizeof(KbChainRec), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hg.data(), ginfo, (size_t)n_groups * sizeof(KbGroupInfo), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int64_t g = 0; g < n_groups; ++g)
+                for (int i = 0; i < hg[(size_t)g].n_chains; ++i) {
+                    const KbChainRec &c = hch[(size_t)(hg[(size_t)g].chain_base + i)];
+                    int32_t rec[10] = {hg[(size_t)g].asm_id, hg[(size_t)g].gene, c.score, c.cnt, c.rev, c.rid, c.rs, c.re, c.qs, c.qe};
+                    R->chain_dump.insert(R->chain_dump.end(), rec, rec + 10);
+                }
+            P.release(tmp), P.release(nseed), P.release(aoff);
+        }
+        P.release(skey), P.release(sval), P.release(gstart), P.release(occ32);
+        P.release(W.x), P.release(W.y), P.release(W.f), P.release(W.p), P.release(W.v), P.release(W.t), P.release(W.z), P.release(W.u);
+
+        // ---------------- alignment
+        int64_t raw_cap = n_chains + n_anchors / 3 + 16;
+        KbRawHit *raw = P.get<KbRawHit>((size_t)raw_cap);
+        int64_t pool_cap = raw_cap * 24 + (1 << 16);
+        int64_t n_raw = 0, n_pool = 0;
+        uint32_t *pool = nullptr;
+        size_t sbytes = kb_align_scratch_bytes(p.max_sw_cells);
+        int n_warps = bt->n_sm * 16;
+        {
+            int64_t need_warps = ((n_chains + 3) / 4) * 4;
+            if (need_warps < 4) need_warps = 4;
+            if (n_warps > need_warps) n_warps = (int)need_warps;
+        }
+        uint8_t *scratch = P.get<uint8_t>((size_t)n_warps * sbytes);
+        unsigned long long *d_next = P.get<unsigned long long>(1);
+        for (int attempt = 0;; ++attempt) {
+            CU(cudaMalloc((void **)&pool, (size_t)pool_cap * 4 + 16));
+            CU(cudaMemsetAsync(d_next, 0, 8, st));
+            CU(cudaMemsetAsync(d_counters + 4, 0, 16, st));
+            CU(cudaMemsetAsync(d_counters + 8, 0, 8, st));
+            kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next, st);
+            ++launches;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            n_raw = (int64_t)hc[4], n_pool = (int64_t)hc[5];
+            if (n_raw > raw_cap) throw std::string("raw hit buffer overflow");
+            if (n_pool <= pool_cap) break;
+            if (attempt >= 1) throw std::string("cigar pool overflow");
+            // NB: the seed-filter flags written into cy[] are idempotent, so the stage can simply be re-run
+            CU(cudaFree(pool));
+            pool_cap = n_pool + 1024;
+        }
+        R->pool = pool, R->owned.push_back(pool), R->n_cigar = n_pool;
+        P.release(scratch);
+        CU(cudaEventRecord(ev[4], st));
+        R->counters[4] = n_raw, R->counters[6] = (int64_t)hc[8];
+
+        // ---------------- finalise: order raw hits by (group, reg, split), per-query filter/sort/parent/mapq, compact to SoA
+        KbRawHit *sorted = P.get<KbRawHit>((size_t)n_raw + 1);
+        int32_t *keep = P.get<int32_t>((size_t)n_raw + 1);
+        int64_t *oidx = P.get<int64_t>((size_t)n_raw + 1);
+        int64_t n_hits = 0;
+        if (n_raw > 0) {
+            uint64_t *rk = P.get<uint64_t>((size_t)n_raw), *rk2 = P.get<uint64_t>((size_t)n_raw);
+            uint32_t *ri = P.get<uint32_t>((size_t)n_raw), *ri2 = P.get<uint32_t>((size_t)n_raw);
+            kb_launch_rawkey(raw, n_raw, rk, ri, st);
+            size_t tb = kb_sort_pairs_temp_bytes(n_raw), tb2 = kb_scan_temp_bytes(n_raw);
+            if (tb2 > tb) tb = tb2;
+            uint8_t *tmp = P.get<uint8_t>(tb);
+            CU(kb_sort_pairs(tmp, tb, rk, rk2, ri, ri2, n_raw, 64, st));
+            kb_launch_gather_raw(raw, ri2, n_raw, sorted, st);
+            int32_t *fw = P.get<int32_t>((size_t)n_raw + 1);
+            uint64_t *fcov = P.get<uint64_t>((size_t)n_raw + 1);
+            kb_launch_finalize(p, sorted, n_raw, ginfo, fw, fcov, keep, st);
+            CU(kb_exclusive_sum(tmp, tb, keep, oidx, n_raw, st));
+            launches += 14;
+            int64_t last_o = 0;
+            int32_t last_k = 0;
+            CU(cudaMemcpyAsync(&last_o, oidx + n_raw - 1, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(&last_k, keep + n_raw - 1, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            n_hits = last_o + last_k;
+        }
+        R->n_hits = n_hits;
+        {
+            size_t n = (size_t)n_hits + 1;
+            auto own = [&](size_t bytes) {
+                void *q = nullptr;
+                CU(cudaMalloc(&q, bytes));
+                R->owned.push_back(q);
+                return q;
+            };
+            kb_hits_t &d = R->d;
+            d.capacity = n_hits;
+            d.asm_id = (int32_t *)own(n * 4), d.gene = (int32_t *)own(n * 4), d.q_start = (int32_t *)own(n * 4), d.q_end = (int32_t *)own(n * 4);
+            d.t_ctg = (int32_t *)own(n * 4), d.t_len = (int32_t *)own(n * 4), d.t_start = (int32_t *)own(n * 4), d.t_end = (int32_t *)own(n * 4);
+            d.strand = (int8_t *)own(n), d.score = (int32_t *)own(n * 4), d.matches = (int32_t *)own(n * 4), d.block_len = (int32_t *)own(n * 4);
+            d.edit_distance = (int32_t *)own(n * 4), d.mapq = (uint8_t *)own(n), d.is_primary = (uint8_t *)own(n);
+            d.cigar_off = (int64_t *)own(n * 8), d.n_cigar = (int32_t *)own(n * 4);
+            kb_launch_scatter(sorted, keep, oidx, n_raw, ginfo, bv, d, st);
+            ++launches;
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(ev[5], st));
+        CU(cudaStreamSynchronize(st));
+        R->counters[5] = launches;
+        for (int s = 0; s < KB_STAGE_TOTAL; ++s) CU(cudaEventElapsedTime(&R->stage_ms[s], ev[s], ev[s + 1]));
+        CU(cudaEventElapsedTime(&R->stage_ms[KB_STAGE_TOTAL], ev[0], ev[5]));
+        P.clear();
+        CU(cudaStreamSynchronize(st));
+        for (auto &e : ev) cudaEventDestroy(e);
+        cudaStreamDestroy(st);
+    } catch (const std::string &e) {
+        P.clear();
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        for (auto &e2 : ev)
+            if (e2) cudaEventDestroy(e2);
+        kb_result_destroy(R);
+        return fail(KB_ERR_CUDA, e);
+    }
+    *out = R;
+    return KB_OK;
+}
+
+extern "C" {
+
+int kb_map_batch(const kb_index_t *ix, const kb_batch_t *bt, kb_result_t **out)
+{
+    if (!ix || !bt || !out) return fail(KB_ERR_ARG, "null argument");
+    const char *ks = getenv("KAPTIVE_B200_KEEP_STAGES");
+    return map_batch_impl(ix, const_cast<kb_batch *>(bt), out, ks && ks[0] == '1');
+}
+
+int kb_result_size(const kb_result_t *r, int64_t *n_hits, int64_t *n_cigar)
+{
+    if (!r) return fail(KB_ERR_ARG, "null result");
+    if (n_hits) *n_hits = r->n_hits;
+    if (n_cigar) *n_cigar = r->n_cigar;
+    return KB_OK;
+}
+
+int kb_result_fetch(const kb_result_t *r, kb_hits_t *dst, uint32_t *cigar, int64_t cigar_cap)
+{
+    if (!r || !dst) return fail(KB_ERR_ARG, "null argument");
+    if (dst->capacity < r->n_hits) return fail(KB_ERR_CAPACITY, "hit arrays smaller than kb_result_size()");
+    if (cigar && cigar_cap < r->n_cigar) return fail(KB_ERR_CAPACITY, "cigar buffer smaller than kb_result_size()");
+    try {
+        CU(cudaSetDevice(r->device));
+        const size_t n = (size_t)r->n_hits;
+        const kb_hits_t &d = r->d;
+#define CP(f, sz) \
+    if (dst->f && n) CU(cudaMemcpy(dst->f, d.f, n * (sz), cudaMemcpyDeviceToHost))
+        CP(asm_id, 4); CP(gene, 4); CP(q_start, 4); CP(q_end, 4); CP(t_ctg, 4); CP(t_len, 4); CP(t_start, 4); CP(t_end, 4);
+        CP(strand, 1); CP(score, 4); CP(matches, 4); CP(block_len, 4); CP(edit_distance, 4); CP(mapq, 1); CP(is_primary, 1);
+        CP(cigar_off, 8); CP(n_cigar, 4);
+#undef CP
+        if (cigar && r->n_cigar) CU(cudaMemcpy(cigar, r->pool, (size_t)r->n_cigar * 4, cudaMemcpyDeviceToHost));
+    } catch (const std::string &e) {
+        return fail(KB_ERR_CUDA, e);
+    }
+    return KB_OK;
+}
+
+int kb_result_stage_ms(const kb_result_t *r, float *ms)
+{
+    if (!r || !ms) return fail(KB_ERR_ARG, "null argument");
+    memcpy(ms, r->stage_ms, sizeof(r->stage_ms));
+    return KB_OK;
+}
+int kb_result_counters(const kb_result_t *r, int64_t *c)
+{
+    if (!r || !c) return fail(KB_ERR_ARG, "null argument");
+    memcpy(c, r->counters, sizeof(r->counters));
+    return KB_OK;
+}
+int kb_result_mid_occ(const kb_result_t *r, int32_t *out)
+{
+    if (!r || !out) return fail(KB_ERR_ARG, "null argument");
+    if (!r->mid_occ.empty()) memcpy(out, r->mid_occ.data(), r->mid_occ.size() * 4);
+    return KB_OK;
+}
+int kb_result_fetch_anchors(const kb_result_t *r, int32_t *out, int64_t cap, int64_t *n)
+{
+    if (!r || !n) return fail(KB_ERR_ARG, "null argument");
+    *n = r->n_anchor_dump;
+    if (!out) return KB_OK;
+    if (cap < r->n_anchor_dump) return fail(KB_ERR_CAPACITY, "anchor dump buffer too small");
+    if (r->n_anchor_dump) {
+        cudaSetDevice(r->device);
+        if (cudaMemcpy(out, r->d_anchor_dump, (size_t)r->n_anchor_dump * 28, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(KB_ERR_CUDA, "copy of the anchor dump failed");
+    }
+    return KB_OK;
+}
+int kb_result_fetch_chains(const kb_result_t *r, int32_t *out, int64_t cap, int64_t *n)
+{
+    if (!r || !n) return fail(KB_ERR_ARG, "null argument");
+    *n = (int64_t)r->chain_dump.size() / 10;
+    if (!out) return KB_OK;
+    if (cap < *n) return fail(KB_ERR_CAPACITY, "chain dump buffer too small");
+    if (*n) memcpy(out, r->chain_dump.data(), r->chain_dump.size() * 4);
+    return KB_OK;
+}
+
+int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
+                      const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
+                      int64_t cigar_cap, int64_t *n_cigar)
+{
+    if (!ix) return fail(KB_ERR_ARG, "null index");
+    kb_batch_t *b = nullptr;
+    int rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
+    if (rc) return rc;
+    kb_result_t *r = nullptr;
+    rc = kb_map_batch(ix, b, &r);
+    if (rc == KB_OK) {
+        if (n_hits) *n_hits = r->n_hits;
+        if (n_cigar) *n_cigar = r->n_cigar;
+        if (dst) rc = kb_result_fetch(r, dst, cigar, cigar_cap);
+        kb_result_destroy(r);
+    }
+    kb_batch_destroy(b);
+    return rc;
+}
+
+int kb_scan_minimizers(const kb_index_t *ix, const kb_batch_t *bt, int32_t asm_id, uint32_t *hash, int32_t *ctg, uint32_t *pos_strand,
+                       int64_t cap, int64_t *n)
+{
+    if (!ix || !bt || !n) return fail(KB_ERR_ARG, "null argument");
+    if (asm_id < 0 || asm_id >= bt->L.n_asm) return fail(KB_ERR_ARG, "assembly index out of range");
+    cudaStream_t st = nullptr;
+    DevPool P;
+    try {
+        CU(cudaSetDevice(ix->device));
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        P.st = st;
+        unsigned long long *dc = P.get<unsigned long long>(KB_N_COUNTERS);
+        CU(cudaMemsetAsync(dc, 0, KB_N_COUNTERS * 8, st));
+        uint32_t *dh = P.get<uint32_t>((size_t)cap + 1), *dp = P.get<uint32_t>((size_t)cap + 1);
+        int32_t *dcg = P.get<int32_t>((size_t)cap + 1);
+        kb_launch_scan(ix->view, bt->view, nullptr, nullptr, dc + 16, 0, dh, dcg, dp, cap, asm_id, bt->n_sm, st);
+        CU(cudaGetLastError());
+        unsigned long long cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, dc + 23, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *n = (int64_t)cnt;
+        int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
+        if (m > 0 && hash) CU(cudaMemcpy(hash, dh, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        if (m > 0 && ctg) CU(cudaMemcpy(ctg, dcg, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        if (m > 0 && pos_strand) CU(cudaMemcpy(pos_strand, dp, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        P.clear();
+        CU(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+    } catch (const std::string &e) {
+        P.clear();
+        if (st) cudaStreamDestroy(st);
+        return fail(KB_ERR_CUDA, e);
+    }
+    return KB_OK;
+}
+
+int kb_bench_scan(const kb_index_t *ix, const kb_batch_t *bt, int iters, float *mean_ms, int64_t *n_anchors_out)
+{
+    if (!ix || !bt || !mean_ms || iters <= 0) return fail(KB_ERR_ARG, "bad argument");
+    cudaStream_t st = nullptr;
+    DevPool P;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    try {
+        CU(cudaSetDevice(ix->device));
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        P.st = st;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        int64_t cap = bt->last_anchor_count > 0 ? bt->last_anchor_count + 1024 : bt->view.total_bases / 48 + (1 << 20);
+        unsigned long long *dc = P.get<unsigned long long>(KB_N_COUNTERS);
+        uint64_t *akey = P.get<uint64_t>((size_t)cap);
+        uint32_t *aval = P.get<uint32_t>((size_t)cap);
+        CU(cudaMemsetAsync(dc, 0, KB_N_COUNTERS * 8, st));
+        kb_launch_scan(ix->view, bt->view, akey, aval, dc, cap, nullptr, nullptr, nullptr, 0, -1, bt->n_sm, st);  // warm-up
+        CU(cudaStreamSynchronize(st));
+        CU(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) {
+            CU(cudaMemsetAsync(dc, 0, KB_N_COUNTERS * 8, st));
+            kb_launch_scan(ix->view, bt->view, akey, aval, dc, cap, nullptr, nullptr, nullptr, 0, -1, bt->n_sm, st);
+        }
+        CU(cudaEventRecord(e1, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        *mean_ms = ms / (float)iters;
+        unsigned long long hc[KB_N_COUNTERS];
+        CU(cudaMemcpy(hc, dc, sizeof hc, cudaMemcpyDeviceToHost));
+        if (n_anchors_out) *n_anchors_out = (int64_t)hc[1];
+        P.clear();
+        CU(cudaStreamSynchronize(st));
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        cudaStreamDestroy(st);
+    } catch (const std::string &e) {
+        P.clear();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+        return fail(KB_ERR_CUDA, e);
+    }
+    return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// kb_pipeline.cu -- kernels after the seeding scan: ASCII packing, group discovery, chaining
+// (one thread per query group), base-level alignment (one warp per chain, persistent,
+// dynamic work queue), per-query finalisation and the SoA scatter.  Sorting / selection /
+// prefix sums between the stages are CUB device primitives (plumbing, like cuBLAS would be
+// for a GEMM); every stage that carries the path's arithmetic is the hand-written logic in
+// kb_scan.cuh / kb_chain.cuh / kb_align.cuh / kb_final.cuh.
+#include <cub/cub.cuh>
+#include "kb_final.cuh"
+#include "kb_kernels.h"
+
+// ------------------------------------------------------------------ pack: ASCII -> 2 bit + N mask
+// One thread per 32 bases of storage (2 sequence words + 1 mask word).  Storage of a contig is
+// padded to 64 bases; padding is marked ambiguous.
+__global__ void kb_pack_kernel(const uint8_t *ascii, int64_t ascii_base, const int64_t *ctg_off, const int64_t *ctg_soff,
+                               const int32_t *ctg_len, int32_t ctg_begin, int32_t ctg_end, int64_t grp_begin, int64_t grp_end,
+                               uint32_t *seq2, uint32_t *nmask)
+{
+    for (int64_t g = grp_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < grp_end; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b0 = g << 5;
+        // contig whose storage contains b0: last c in [ctg_begin, ctg_end) with soff[c] <= b0
+        int lo = ctg_begin, hi = ctg_end - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (ctg_soff[mid] <= b0) lo = mid;
+            else hi = mid - 1;
+        }
+        uint32_t w0 = 0, w1 = 0, m = 0xffffffffu;
+        const int64_t rel = b0 - ctg_soff[lo];
+        const int32_t L = ctg_len[lo];
+        if (rel >= 0 && rel < L) {
+            const uint8_t *s = ascii + (ctg_off[lo] - ascii_base) + rel;
+            int n = L - rel < 32 ? (int)(L - rel) : 32;
+            for (int i = 0; i < n; ++i) {
+                uint32_t c = kb_nt4(__ldg(s + i));
+                if (c < 4) {
+                    m &= ~(1u << i);
+                    if (i < 16) w0 |= c << (2 * i);
+                    else w1 |= c << (2 * (i - 16));
+                }
+            }
+        }
+        seq2[2 * g] = w0, seq2[2 * g + 1] = w1, nmask[g] = m;
+    }
+}
+
+void kb_launch_pack(const uint8_t *ascii, int64_t ascii_base, const int64_t *ctg_off, const int64_t *ctg_soff, const int32_t *ctg_len,
+                    int32_t ctg_begin, int32_t ctg_end, int64_t grp_begin, int64_t grp_end, uint32_t *seq2, uint32_t *nmask,
+                    cudaStream_t st)
+{
+    int64_t n = grp_end - grp_begin;
+    if (n <= 0) return;
+    int64_t grid = (n + 255) / 256;
+    if (grid > 148 * 64) grid = 148 * 64;
+    kb_pack_kernel<<<(unsigned)grid, 256, 0, st>>>(ascii, ascii_base, ctg_off, ctg_soff, ctg_len, ctg_begin, ctg_end, grp_begin, grp_end, seq2, nmask);
+}
+
+// ------------------------------------------------------------------ occurrence counts
+// occ[asm][entry] += 1 for every anchor; flags assemblies in which some gene minimizer occurs more
+// than min_mid_occ times (only those can be affected by the exact value of mid_occ).
+__global__ void kb_occ_kernel(const uint64_t *akey, const uint32_t *aval, int64_t n, int64_t n_entries, uint32_t *occ32,
+                              int32_t min_mid_occ, int32_t *need_census)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t a = (int64_t)(akey[i] >> KB_KEY_ASM_SHIFT);
+        int64_t idx = a * n_entries + aval[i];
+        int sh = (int)(idx & 1) * 16;
+        uint32_t old = atomicAdd(&occ32[idx >> 1], 1u << sh);
+        uint32_t c = ((old >> sh) & 0xffffu) + 1;
+        if (c == (uint32_t)min_mid_occ + 1) need_census[a] = 1;
+        if (c >= 0xfff0u) need_census[a] = 2;  // 16-bit counter about to wrap: reported as a limit error
+    }
+}
+
+void kb_launch_occ(const uint64_t *akey, const uint32_t *aval, int64_t n, int64_t n_entries, uint32_t *occ32, int32_t min_mid_occ,
+                   int32_t *need_census, cudaStream_t st)
+{
+    if (n <= 0) return;
+    int64_t grid = (n + 255) / 256;
+    if (grid > 148 * 32) grid = 148 * 32;
+    kb_occ_kernel<<<(unsigned)grid, 256, 0, st>>>(akey, aval, n, n_entries, occ32, min_mid_occ, need_census);
+}
+
+// ------------------------------------------------------------------ group discovery
+__global__ void kb_group_flag_kernel(const uint64_t *skey, int64_t n, uint8_t *flag)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || (skey[i] >> KB_KEY_GENE_SHIFT) != (skey[i - 1] >> KB_KEY_GENE_SHIFT)) ? 1 : 0;
+}
+
+size_t kb_sort_pairs_temp_bytes(int64_t n)
+{
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n, 0, 64);
+    return b;
+}
+cudaError_t kb_sort_pairs(void *tmp, size_t tmp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout,
+                          int64_t n, int end_bit, cudaStream_t st)
+{
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, n, 0, end_bit, st);
+}
+size_t kb_sort_keys32_temp_bytes(int64_t n)
+{
+    size_t b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32);
+    return b;
+}
+cudaError_t kb_sort_keys32(void *tmp, size_t tmp_bytes, const uint32_t *kin, uint32_t *kout, int64_t n, int end_bit, cudaStream_t st)
+{
+    return cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, kin, kout, n, 0, end_bit, st);
+}
+size_t kb_select_temp_bytes(int64_t n)
+{
+    size_t b = 0;
+    cub::CountingInputIterator<int64_t> it(0);
+    cub::DeviceSelect::Flagged(nullptr, b, it, (const uint8_t *)nullptr, (int64_t *)nullptr, (int64_t *)nullptr, n);
+    return b;
+}
+cudaError_t kb_select_flagged(void *tmp, size_t tmp_bytes, const uint8_t *flag, int64_t *out, int64_t *n_out, int64_t n, cudaStream_t st)
+{
+    cub::CountingInputIterator<int64_t> it(0);
+    return cub::DeviceSelect::Flagged(tmp, tmp_bytes, it, flag, out, n_out, n, st);
+}
+size_t kb_scan_temp_bytes(int64_t n)
+{
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int32_t *)nullptr, (int64_t *)nullptr, n);
+    return b;
+}
+cudaError_t kb_exclusive_sum(void *tmp, size_t tmp_bytes, const int32_t *in, int64_t *out, int64_t n, cudaStream_t st)
+{
+    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, n, st);
+}
+size_t kb_rle_temp_bytes(int64_t n)
+{
+    size_t b = 0;
+    cub::DeviceRunLengthEncode::Encode(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t *)nullptr, n);
+    return b;
+}
+cudaError_t kb_rle(void *tmp, size_t tmp_bytes, const uint32_t *in, uint32_t *uniq, uint32_t *counts, int64_t *n_runs, int64_t n, cudaStream_t st)
+{
+    return cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, in, uniq, counts, n_runs, n, st);
+}
+
+// ------------------------------------------------------------------ chaining: one thread per group
+__global__ void __launch_bounds__(128) kb_chain_kernel(KbIndexView ix, KbBatchView bt, const uint64_t *skey, const uint32_t *sval,
+                                                       const int64_t *gstart, int64_t n_groups, int64_t n_anchors,
+                                                       const uint16_t *occ, const int32_t *mid_occ, KbChainWork W, uint64_t *cx,
+                                                       uint64_t *cy, KbGroupInfo *ginfo, KbChainRec *chains,
+                                                       unsigned long long *counters, int64_t chain_cap)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    int64_t gs = gstart[g], ge = g + 1 < n_groups ? gstart[g + 1] : n_anchors;
+    kb_chain_group(ix, bt, skey, sval, gs, ge, occ, mid_occ, W, cx, cy, &ginfo[g], chains, &counters[3], chain_cap, (int32_t)g);
+}
+
+void kb_launch_chain(const KbIndexView &ix, const KbBatchView &bt, const uint64_t *skey, const uint32_t *sval, const int64_t *gstart,
+                     int64_t n_groups, int64_t n_anchors, const uint16_t *occ, const int32_t *mid_occ, const KbChainWork &W,
+                     uint64_t *cx, uint64_t *cy, KbGroupInfo *ginfo, KbChainRec *chains, unsigned long long *counters,
+                     int64_t chain_cap, cudaStream_t st)
+{
+    if (n_groups <= 0) return;
+    kb_chain_kernel<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ix, bt, skey, sval, gstart, n_groups, n_anchors, occ, mid_occ,
+                                                                        W, cx, cy, ginfo, chains, counters, chain_cap);
+}
+
+// ------------------------------------------------------------------ alignment: one warp per chain, persistent
+__global__ void __launch_bounds__(128) kb_align_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
+                                                       const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, uint8_t *scratch,
+                                                       size_t scratch_bytes, KbRawHit *raw, int64_t raw_cap, uint32_t *pool,
+                                                       int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
+    int64_t cells = 0;
+    for (;;) {
+        unsigned long long ci = 0;
+        if (lane == 0) ci = atomicAdd(next_chain, 1ull);
+        ci = __shfl_sync(0xffffffffu, ci, 0);
+        if ((int64_t)ci >= n_chains) break;
+        const KbChainRec c = chains[ci];
+        const KbGroupInfo gi = ginfo[c.group];
+        KbReg r;
+        const int reg_idx = (int)((int64_t)ci - gi.chain_base);
+        r.as = c.as, r.cnt = c.cnt, r.score = c.score, r.score0 = c.score0, r.mlen = c.mlen, r.blen = c.blen, r.parent = c.parent, r.id = reg_idx;
+        r.hash = c.hash, r.rev = c.rev, r.rid = c.rid, r.rs = c.rs, r.re = c.re, r.qs = c.qs, r.qe = c.qe;
+        r.has_p = 0, r.dp_score = 0, r.dp_max = 0, r.n_ambi = 0, r.n_cigar = 0;
+        for (int split = 0;; ++split) {
+            KbReg r2;
+            r2.cnt = 0;
+            int e = kb_align1<32>(ix, bt, lane, gi.asm_id, gi.gene, r, r2, gi.n_a, cx + gi.a_base, cy + gi.a_base, S, &cells);
+            const int ncg = e ? 0 : r.n_cigar;
+            unsigned long long slot = 0, coff = 0;
+            if (lane == 0) {
+                slot = atomicAdd(&counters[4], 1ull);
+                coff = atomicAdd(&counters[5], (unsigned long long)ncg);
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            coff = __shfl_sync(0xffffffffu, coff, 0);
+            if ((int64_t)slot < raw_cap && lane == 0) {
+                KbRawHit h;
+                h.group = c.group, h.reg_idx = reg_idx, h.split_idx = split;
+                h.cnt = r.cnt, h.score = r.score, h.score0 = r.score0, h.hash = r.hash;
+                h.rev = r.rev, h.rid = r.rid, h.rs = r.rs, h.re = r.re, h.qs = r.qs, h.qe = r.qe;
+                h.has_p = r.has_p, h.dp_score = r.dp_score, h.dp_max = r.dp_max, h.dp_max2 = 0, h.n_ambi = r.n_ambi, h.mlen = r.mlen, h.blen = r.blen;
+                h.parent = r.parent, h.subsc = c.subsc, h.n_sub = c.n_sub, h.mapq = 0, h.n_cigar = ncg, h.cigar_off = (int64_t)coff;
+                h.err = e, h.pad = 0;
+                raw[slot] = h;
+            }
+            if ((int64_t)(coff + ncg) <= pool_cap)
+                for (int i = lane; i < ncg; i += 32) pool[coff + i] = S.cigar[i];
+            __syncwarp();
+            if (e == 0 && r2.cnt > 0) r = r2;
+            else break;
+        }
+    }
+    if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
+}
+
+void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
+                     const uint64_t *cx, uint64_t *cy, uint8_t *scratch, size_t scratch_bytes, int n_warps, KbRawHit *raw,
+                     int64_t raw_cap, uint32_t *pool, int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain,
+                     cudaStream_t st)
+{
+    if (n_chains <= 0) return;
+    kb_align_kernel<<<(unsigned)(n_warps / 4), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, scratch, scratch_bytes, raw, raw_cap,
+                                                             pool, pool_cap, counters, next_chain);
+}
+
+// ------------------------------------------------------------------ finalisation
+__global__ void kb_rawkey_kernel(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const KbRawHit &h = raw[i];
+        key[i] = (uint64_t)(uint32_t)h.group << 32 | (uint64_t)(h.reg_idx & 0xfffff) << 12 | (uint64_t)(h.split_idx & 0xfff);
+        idx[i] = (uint32_t)i;
+    }
+}
+__global__ void kb_gather_raw_kernel(const KbRawHit *raw, const uint32_t *idx, int64_t n, KbRawHit *out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = raw[idx[i]];
+}
+// thread i works only if sorted hit i is the first of its query group
+__global__ void __launch_bounds__(128) kb_finalize_kernel(kb_params_t P, KbRawHit *hits, int64_t n, const KbGroupInfo *ginfo, int32_t *w,
+                                                          uint64_t *cov, int32_t *keep_flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i > 0 && hits[i - 1].group == hits[i].group) return;
+    int64_t e = i + 1;
+    while (e < n && hits[e].group == hits[i].group) ++e;
+    const int32_t grp = hits[i].group;
+    int kept = kb_finalize_group(P, static_cast<KbHitView *>(hits + i), (int)(e - i), ginfo[grp].rep_len, w + i, cov + i);
+    for (int64_t j = i; j < e; ++j) {
+        keep_flag[j] = (j - i) < kept ? 1 : 0;
+        hits[j].group = grp;                         // dropped slots keep the group id so segment detection stays valid
+        if ((j - i) < kept) hits[j].pad = (int32_t)(j - i);  // rank within the query
+    }
+}
+__global__ void kb_scatter_kernel(const KbRawHit *hits, const int32_t *keep_flag, const int64_t *out_idx, int64_t n,
+                                  const KbGroupInfo *ginfo, KbBatchView bt, kb_hits_t o)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!keep_flag[i]) continue;
+        const KbRawHit &h = hits[i];
+        const KbGroupInfo &gi = ginfo[h.group];
+        const int64_t k = out_idx[i];
+        o.asm_id[k] = gi.asm_id, o.gene[k] = gi.gene;
+        o.q_start[k] = h.qs, o.q_end[k] = h.qe;
+        o.t_ctg[k] = h.rid, o.t_len[k] = bt.ctg_len[bt.asm_ctg_start[gi.asm_id] + h.rid], o.t_start[k] = h.rs, o.t_end[k] = h.re;
+        o.strand[k] = h.rev ? -1 : 1;
+        o.score[k] = h.dp_score, o.matches[k] = h.mlen, o.block_len[k] = h.blen, o.edit_distance[k] = h.blen - h.mlen + h.n_ambi;
+        o.mapq[k] = (uint8_t)h.mapq, o.is_primary[k] = (uint8_t)(h.parent == h.pad);
+        o.cigar_off[k] = h.cigar_off, o.n_cigar[k] = h.n_cigar;
+    }
+}
+
+void kb_launch_rawkey(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx, cudaStream_t st)
+{
+    if (n > 0) kb_rawkey_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, n, key, idx);
+}
+void kb_launch_gather_raw(const KbRawHit *raw, const uint32_t *idx, int64_t n, KbRawHit *out, cudaStream_t st)
+{
+    if (n > 0) kb_gather_raw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, idx, n, out);
+}
+void kb_launch_finalize(const kb_params_t &P, KbRawHit *hits, int64_t n, const KbGroupInfo *ginfo, int32_t *w, uint64_t *cov,
+                        int32_t *keep_flag, cudaStream_t st)
+{
+    if (n > 0) kb_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, hits, n, ginfo, w, cov, keep_flag);
+}
+void kb_launch_scatter(const KbRawHit *hits, const int32_t *keep_flag, const int64_t *out_idx, int64_t n, const KbGroupInfo *ginfo,
+                       const KbBatchView &bt, const kb_hits_t &o, cudaStream_t st)
+{
+    if (n > 0) kb_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hits, keep_flag, out_idx, n, ginfo, bt, o);
+}
+void kb_launch_group_flag(const uint64_t *skey, int64_t n, uint8_t *flag, cudaStream_t st)
+{
+    if (n > 0) {
+        int64_t grid = (n + 255) / 256;
+        if (grid > 148 * 32) grid = 148 * 32;
+        kb_group_flag_kernel<<<(unsigned)grid, 256, 0, st>>>(skey, n, flag);
+    }
+}
+
+// ------------------------------------------------------------------ stage dumps for parity tests
+__global__ void kb_dump_anchors_kernel(KbBatchView bt, const KbGroupInfo *ginfo, int64_t n_groups, const int64_t *gstart,
+                                       const uint32_t *wx, const int32_t *wy, const int64_t *out_off, int32_t *out)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const KbGroupInfo &gi = ginfo[g];
+    for (int32_t i = 0; i < gi.n_seed; ++i) {
+        uint32_t xv = wx[gstart[g] + i];
+        int32_t yv = wy[gstart[g] + i];
+        int32_t vpos = (int32_t)(xv & KB_VPOS_MASK);
+        int32_t c = kb_vpos_to_ctg(bt, gi.asm_id, vpos);
+        int32_t *o = out + (out_off[g] + i) * 7;
+        o[0] = gi.asm_id, o[1] = gi.gene, o[2] = (int32_t)(xv >> KB_KEY_REV_SHIFT), o[3] = c - bt.asm_ctg_start[gi.asm_id];
+        o[4] = vpos - bt.ctg_vstart[c], o[5] = yv & 0x3fffffff, o[6] = (yv >> 30) & 1;
+    }
+}
+__global__ void kb_group_nseed_kernel(const KbGroupInfo *ginfo, int64_t n_groups, int32_t *n_seed)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_groups) n_seed[g] = ginfo[g].n_seed;
+}
+void kb_launch_group_nseed(const KbGroupInfo *ginfo, int64_t n_groups, int32_t *n_seed, cudaStream_t st)
+{
+    if (n_groups > 0) kb_group_nseed_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(ginfo, n_groups, n_seed);
+}
+void kb_launch_dump_anchors(const KbBatchView &bt, const KbGroupInfo *ginfo, int64_t n_groups, const int64_t *gstart, const uint32_t *wx,
+                            const int32_t *wy, const int64_t *out_off, int32_t *out, cudaStream_t st)
+{
+    if (n_groups > 0) kb_dump_anchors_kernel<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(bt, ginfo, n_groups, gstart, wx, wy, out_off, out);
+}
