@@ -304,7 +304,7 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
             }
             if (bytes > 0) CU(cudaMemcpyAsync(d_ascii, contig_seqs + lo, (size_t)bytes, cudaMemcpyDefault, st));
             int64_t g0 = L.ctg_soff[c0] >> 5;
-            int64_t g1 = (c1 < L.n_ctg ? L.ctg_soff[c1] : L.storage_bases - 64) >> 5;
+            int64_t g1 = (c1 < L.n_ctg ? L.ctg_soff[c1] : L.storage_bases - 128) >> 5;
             kb_launch_pack(d_ascii, lo, d_off, v.ctg_soff, v.ctg_len, c0, c1, g0, g1, b->seq2, b->nmask, st);
             CU(cudaGetLastError());
             c0 = c1;

@@ -234,7 +234,7 @@ struct KbBatchView {
     int64_t total_bases;
     const uint32_t *seq2;        // 16 bases per word, base b at bits 2*(b&15)
     const uint32_t *nmask;       // 32 bases per word, bit set = ambiguous
-    const int64_t *ctg_soff;     // storage offset in bases (multiple of 64)
+    const int64_t *ctg_soff;     // storage offset in bases (multiple of 128)
     const int32_t *ctg_len;
     const int32_t *ctg_asm;
     const int32_t *ctg_vstart;   // virtual position of base 0 within its assembly

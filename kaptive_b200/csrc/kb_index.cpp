@@ -206,7 +206,7 @@ std::string KbHostBatchLayout::build(const int64_t *ctg_off, const int32_t *ctg_
     ctg_len.assign(ctg_len_in, ctg_len_in + n_ctg);
     ctg_soff.resize(n_ctg), ctg_asm.resize(n_ctg), ctg_vstart.resize(n_ctg);
     chunk_ctg.clear(), chunk_start.clear();
-    int64_t soff = 64;  // one padded group in front so look-back loads of the first contig stay in bounds
+    int64_t soff = 128;  // one padded group in front so look-back loads of the first contig stay in bounds
     total_bases = 0;
     for (int a = 0; a < n_asm; ++a) {
         if (asm_ctg_start[a + 1] < asm_ctg_start[a]) return "asm_contig_start must be non-decreasing";
@@ -217,12 +217,12 @@ std::string KbHostBatchLayout::build(const int64_t *ctg_off, const int32_t *ctg_
             ctg_asm[c] = a, ctg_soff[c] = soff, ctg_vstart[c] = (int32_t)v;
             v += (int64_t)L + KB_CTG_VGAP;
             if (v > (int64_t)KB_VPOS_MASK) return "assembly too large for one batch entry (limit 128 Mb incl. 8 kb per contig)";
-            soff += ((int64_t)L + 63) & ~(int64_t)63;
+            soff += ((int64_t)L + 127) & ~(int64_t)127;  // 128 bases = 16 B of mask: keeps uint4 loads of both arrays aligned
             total_bases += L;
             for (int32_t s = 0; s < L; s += KB_CHUNK_BASES) chunk_ctg.push_back(c), chunk_start.push_back(s);
         }
     }
-    storage_bases = soff + 64;
+    storage_bases = soff + 128;
     return "";
 }
 

@@ -10,7 +10,7 @@
 
 // ------------------------------------------------------------------ pack: ASCII -> 2 bit + N mask
 // One thread per 32 bases of storage (2 sequence words + 1 mask word).  Storage of a contig is
-// padded to 64 bases; padding is marked ambiguous.
+// padded to 128 bases; padding is marked ambiguous.
 __global__ void kb_pack_kernel(const uint8_t *ascii, int64_t ascii_base, const int64_t *ctg_off, const int64_t *ctg_soff,
                                const int32_t *ctg_len, int32_t ctg_begin, int32_t ctg_end, int64_t grp_begin, int64_t grp_end,
                                uint32_t *seq2, uint32_t *nmask)

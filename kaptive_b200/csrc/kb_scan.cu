@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
         {
             const uint4 *sp = reinterpret_cast<const uint4 *>(bt.seq2 + ((soff + lstart) >> 4));
             const uint4 *mp = reinterpret_cast<const uint4 *>(bt.nmask + ((soff + lstart) >> 5));
-            const bool in = lstart < clen;  // contig storage is padded to 64 bases: a started 64-base group is in bounds
+            const bool in = lstart < clen;  // contig storage is padded to 128 bases: a started 64-base (sequence) or 128-base (mask) group is in bounds
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint4 v[4], mv[2];
 #pragma unroll
