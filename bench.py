@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- assemblies/s typed against a kpsc_k-shaped gene database (BASELINE.json metric).
+
+A "step" is one pass of the mapping hot path (scan -> sort -> chain -> align -> finalise) over one
+batch of synthetic assemblies.  Default workload = BASELINE.json configs[1]: 1,000 synthetic 5 Mb
+assemblies vs a 150-locus x 20-gene database on one B200.
+
+  value      : assemblies/s with the 2-bit packed batch already resident in HBM (wall clock between
+               device synchronisations, max over ranks; device-event time reported beside it)
+  e2e        : the same metric through the host-buffer C-ABI call (kb_map_assemblies): pinned ASCII
+               contigs -> H2D -> pack -> map -> D2H of the hit arrays, every step
+  roofline   : the seeding scan kernel, algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline / --impl reference : the CPU oracle (a port of the reference's mapper algorithm; the
+               reference's own mapper `rammappy` is a closed Rust wheel that is not installable here)
+               on all host cores over a bounded sample of the same workload
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "assemblies_per_sec_typed_kpsc_k"
+UNIT = "assemblies/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-asm", type=int, default=1000, help="assemblies per GPU per step")
+    ap.add_argument("--asm-len", type=int, default=5_000_000)
+    ap.add_argument("--n-loci", type=int, default=150)
+    ap.add_argument("--genes-per-locus", type=int, default=20)
+    ap.add_argument("--n-core", type=int, default=4)
+    ap.add_argument("--e2e-asm", type=int, default=128, help="assemblies per end-to-end step (host buffers)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a) -> str:
+    return (f"{a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU vs kpsc_k-shaped db "
+            f"({a.n_loci} loci x {a.genes_per_locus} genes, {a.n_core} core families)")
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def _oracle_worker(args):
+    import oracle_lib as ol  # noqa: E402  (test infrastructure; used here only as the timed CPU baseline)
+
+    flat_db, asm_flats = args
+    odb = ol.OracleDB(*flat_db)
+    n = 0
+    for f in asm_flats:
+        n += len(odb.map(*f)["hits"])
+    return n
+
+
+def cpu_oracle_rate(db, asms_flat, cores: int) -> tuple[float, float]:
+    """assemblies/s of the oracle over `asms_flat` with one process per core; returns (rate, seconds)."""
+    import multiprocessing as mp
+
+    flat_db = db.flat()
+    shards = [asms_flat[i::cores] for i in range(cores)]
+    shards = [s for s in shards if s]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(shards)) as pool:
+        pool.map(_oracle_worker, [(flat_db, s) for s in shards])
+    dt = time.perf_counter() - t0
+    return len(asms_flat) / dt, dt
+
+
+def host_sample(a, db, n: int):
+    """n assemblies of the workload as host arrays (generated with the same seeded numpy generator family)."""
+    from kaptive_b200 import synth
+
+    out = []
+    n_real = int(db.gene_locus[~db.extra].max() + 1)
+    for i in range(n):
+        rng = np.random.default_rng(1000 + i)
+        asm = synth.make_assembly(db, int(rng.integers(0, n_real)), seed=1000 + i, genome_len=a.asm_len)
+        out.append(asm.flat())
+    return out
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kaptive_b200 import synth
+
+    cores = os.cpu_count() or 1
+    db = synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1)
+    n = a.cpu_sample or max(2, min(2 * cores, 16))
+    sample = host_sample(a, db, n)
+    for _ in range(min(a.warmup, 1)):
+        cpu_oracle_rate(db, sample[: max(1, min(cores, n))], cores)
+    rates, secs = [], []
+    for _ in range(a.steps):
+        r, s = cpu_oracle_rate(db, sample, cores)
+        rates.append(r), secs.append(s)
+    v = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} assemblies per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} x {a.asm_len / 1e6:g} Mb assemblies, oracle/kb_oracle.c, one process per core"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference mapper (rammappy, closed Rust wheel) is not installable offline; this arm times the C port of its algorithm",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+
+    from kaptive_b200 import mapper, synth, workload
+    from kaptive_b200._lib import check, load, ptr
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+
+    db = synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1)
+    # gene index: built on rank 0, broadcast once as a flat byte image over NCCL
+    if world > 1:
+        if rank == 0:
+            gi0 = mapper.GeneIndex(db.genes, device=local)
+            img = torch.from_numpy(gi0.serialize()).to(dev)
+            n_img = torch.tensor([img.numel()], device=dev, dtype=torch.int64)
+        else:
+            n_img = torch.zeros(1, device=dev, dtype=torch.int64)
+        dist.broadcast(n_img, 0)
+        if rank != 0:
+            img = torch.empty(int(n_img.item()), dtype=torch.uint8, device=dev)
+        dist.broadcast(img, 0)
+        gi = gi0 if rank == 0 else mapper.GeneIndex.deserialize(img.cpu().numpy(), device=local)
+    else:
+        gi = mapper.GeneIndex(db.genes, device=local)
+
+    wl = workload.make_device_workload(db, a.n_asm, a.asm_len, seed=1000, device=dev, first_index=rank * a.n_asm)
+    torch.cuda.synchronize()
+    batch = mapper.AssemblyBatch(wl.ascii.data_ptr(), wl.contig_off, wl.contig_len, wl.asm_contig_start, device=local)
+    packed_bytes = batch.packed_bytes
+
+    # end-to-end inputs: pinned host ASCII of the first e2e_asm assemblies
+    ne = min(a.e2e_asm, a.n_asm)
+    nc_e = int(wl.asm_contig_start[ne])
+    host_ascii = torch.empty(ne * a.asm_len, dtype=torch.uint8).pin_memory()
+    host_ascii.copy_(wl.ascii[: ne * a.asm_len])
+    e_off = np.ascontiguousarray(wl.contig_off[:nc_e])
+    e_len = np.ascontiguousarray(wl.contig_len[:nc_e])
+    e_acs = np.ascontiguousarray(wl.asm_contig_start[: ne + 1])
+    del wl.ascii
+    wl.ascii = None
+    torch.cuda.empty_cache()
+
+    L = load()
+
+    def e2e_step():
+        cap = 4096 * ne
+        h, arrays = mapper.alloc_hits(cap)
+        cig = np.zeros(cap * 24, dtype=np.uint32)
+        nh, ncg = C.c_int64(0), C.c_int64(0)
+        check(L.kb_map_assemblies(gi._h, C.c_void_p(host_ascii.data_ptr()), ptr(e_off), ptr(e_len), ptr(e_acs), ne, C.byref(h),
+                                  C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
+        d2h = sum(v.itemsize for v in arrays.values()) * nh.value + 4 * ncg.value
+        return nh.value, d2h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        gi.map(batch, fetch=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_acc = {}
+    counters = {}
+    n_hits = 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = gi.map(batch, fetch=True)
+        n_hits = len(res)
+        counters = res.counters
+        for k, v in res.stage_ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else {}
+    dev_ms = stage_acc.get("total", 0.0) / a.steps
+    t = torch.tensor([wall, dev_ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, dev_ms_max = float(t[0]), float(t[1])
+    ms_per_step = wall_max / a.steps * 1e3
+    value = a.n_asm * world / (wall_max / a.steps)
+
+    # end-to-end (host buffers) ------------------------------------------------------------------
+    for _ in range(min(a.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(a.steps):
+        _, d2h = e2e_step()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = ne * world / (float(te[0]) / a.steps)
+    h2d = int(host_ascii.numel() + e_off.nbytes + e_len.nbytes + e_acs.nbytes)
+
+    if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # roofline of the scan kernel --------------------------------------------------------------------
+    peak, peak_src = peaks()
+    scan_ms = stage_acc.get("scan", 0.0) / a.steps
+    alg_bytes = packed_bytes + 12 * counters.get("anchors", 0)
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "kb_scan_kernel<10,15>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": scan_ms}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = a.cpu_sample or max(2, min(2 * cores, 16))
+        sample = host_sample(a, db, n)
+        rate, secs = cpu_oracle_rate(db, sample, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} x {a.asm_len / 1e6:g} Mb assemblies of the same generator, oracle/kb_oracle.c, one process per core, {secs:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "parallelism": f"assemblies sharded over {world} GPU(s), gene index broadcast once",
+                   "l2": "inputs larger than L2 (packed batch %.2f GB per GPU)" % (packed_bytes / 1e9),
+                   "hits_per_step": n_hits},
+        "device_ms_per_step": dev_ms_max,
+        "stage_ms": {k: v / a.steps for k, v in stage_acc.items()},
+        "counters": counters,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                "assemblies_per_step": ne},
+        "gpu_launches": int(counters.get("launches", 0)) * a.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

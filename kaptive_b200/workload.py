@@ -1,0 +1,82 @@
+"""Benchmark workloads (BASELINE.json configs) as seeded synthetic inputs, generated on the device.
+
+``configs[1]``: 1,000 synthetic 5 Mb Klebsiella-like assemblies vs a kpsc_k-shaped database
+(150 loci x 20 genes, 4 core gene families shared by all loci) on one B200.
+
+The 5 Gbase of background sequence are drawn with torch on the GPU (numpy would take minutes);
+the embedded locus of each assembly is mutated on the host (small) and copied in.  torch is used
+for device memory and RNG only.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import synth
+
+
+@dataclass
+class DeviceWorkload:
+    ascii: "object"  # torch.uint8 tensor [n_asm * asm_len] on the device
+    contig_off: np.ndarray  # int64
+    contig_len: np.ndarray  # int32
+    asm_contig_start: np.ndarray  # int32, n_asm + 1
+    locus: np.ndarray  # embedded locus per assembly
+    n_asm: int
+    asm_len: int
+
+
+def make_device_workload(db: synth.SynthDB, n_asm: int, asm_len: int = 5_000_000, mean_contigs: float = 80.0,
+                         seed: int = 1000, device: str = "cuda:0", gc: float = 0.57, n_frac: float = 1e-4,
+                         sub: tuple[float, float] = (0.0, 0.05), indel: tuple[float, float] = (0.0, 0.005),
+                         first_index: int = 0) -> DeviceWorkload:
+    import torch
+
+    dev = torch.device(device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    out = torch.empty(n_asm * asm_len, dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev)
+    thr = torch.tensor([(1 - gc) / 2, 0.5, 0.5 + gc / 2], device=dev)  # A | C | G | T cumulative
+    step = max(1, (256 << 20) // asm_len)
+    for a0 in range(0, n_asm, step):
+        a1 = min(n_asm, a0 + step)
+        gen.manual_seed(seed * 1_000_003 + first_index + a0)
+        u = torch.rand((a1 - a0) * asm_len, device=dev, generator=gen)
+        codes = torch.bucketize(u, thr).to(torch.uint8)
+        # order A,C,G,T with P(C)=P(G)=gc/2: buckets [0,(1-gc)/2) A, [.., .5) C, [.5, .5+gc/2) G, rest T
+        seg = out[a0 * asm_len : a1 * asm_len]
+        seg.copy_(lut[codes.long()])
+        if n_frac > 0:
+            m = torch.rand(seg.numel(), device=dev, generator=gen) < n_frac
+            seg[m] = ord("N")
+        del u, codes
+    loci = np.zeros(n_asm, dtype=np.int32)
+    ctg_off, ctg_len, acs = [], [], [0]
+    n_real_loci = int((~db.extra).sum() and (db.gene_locus[~db.extra].max() + 1))
+    for a in range(n_asm):
+        rng = np.random.default_rng(seed + first_index + a)
+        li = int(rng.integers(0, n_real_loci))
+        loci[a] = li
+        ls = np.frombuffer(db.loci[li], dtype=np.uint8)
+        ls = synth.mutate(rng, ls, float(rng.uniform(*sub)), float(rng.uniform(*indel)))
+        if rng.random() < 0.5:
+            ls = synth.revcomp(ls)
+        pos = int(rng.integers(0, asm_len - len(ls)))
+        out[a * asm_len + pos : a * asm_len + pos + len(ls)] = torch.from_numpy(ls.copy()).to(dev)
+        n_ctg = max(1, int(rng.poisson(mean_contigs)))
+        bps = np.unique(rng.integers(1, asm_len, size=n_ctg - 1)) if n_ctg > 1 else np.zeros(0, dtype=np.int64)
+        bounds = np.concatenate([[0], bps, [asm_len]]).astype(np.int64)
+        ctg_off.append(a * asm_len + bounds[:-1])
+        ctg_len.append(np.diff(bounds))
+        acs.append(acs[-1] + len(bounds) - 1)
+    return DeviceWorkload(
+        ascii=out,
+        contig_off=np.concatenate(ctg_off).astype(np.int64),
+        contig_len=np.concatenate(ctg_len).astype(np.int32),
+        asm_contig_start=np.array(acs, dtype=np.int32),
+        locus=loci,
+        n_asm=n_asm,
+        asm_len=asm_len,
+    )
