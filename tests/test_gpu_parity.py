@@ -1,0 +1,201 @@
+"""GPU tier (pytest -m gpu): the CUDA path, called through the C-ABI, against the committed golden vectors, the
+oracle, and size-independent properties at full assembly size."""
+
+import ctypes as C
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = np.load(ROOT / "tests/golden/mapping_golden.npz")
+ROWS = json.loads((ROOT / "tests/golden/kaptive_rows.json").read_text())
+FIELDS = ("gene", "q_start", "q_end", "t_ctg", "t_len", "t_start", "t_end", "strand", "score", "matches", "block_len",
+          "edit_distance", "mapq", "is_primary")
+
+
+@pytest.fixture(scope="module")
+def env():
+    os.environ["KAPTIVE_B200_KEEP_STAGES"] = "1"
+    os.environ["KAPTIVE_B200_FORCE_CENSUS"] = "1"
+    from kaptive_b200 import mapper
+
+    names = list(cases.CASES)
+    built = {n: cases.CASES[n]() for n in names}
+    db = built[names[0]][0]
+    assert all(b[0] is db for b in built.values())
+    gi = mapper.GeneIndex(db.genes)
+    res = gi.map_contigs([[s for _, s in built[n][1]] for n in names])
+    yield {"mapper": mapper, "names": names, "built": built, "db": db, "gi": gi, "res": res}
+    os.environ.pop("KAPTIVE_B200_KEEP_STAGES", None)
+    os.environ.pop("KAPTIVE_B200_FORCE_CENSUS", None)
+
+
+def check_against(res, ai, hits, cigar):
+    idx = np.nonzero(res.hits["asm_id"] == ai)[0]
+    assert len(idx) == len(hits)
+    for f in FIELDS:
+        assert np.array_equal(res.hits[f][idx].astype(np.int64), hits[f].astype(np.int64)), f
+    for k, i in enumerate(idx):
+        h = hits[k]
+        assert np.array_equal(res.cigar_of(i), cigar[h["cigar_off"] : h["cigar_off"] + h["n_cigar"]])
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_gpu_matches_golden(env, name):
+    ai = env["names"].index(name)
+    check_against(env["res"], ai, GOLD[f"{name}/hits"], GOLD[f"{name}/cigar"])
+    mid, n_mz, n_anchor = (int(x) for x in GOLD[f"{name}/meta"])
+    assert int(env["res"].mid_occ[ai]) == mid
+    chains = env["res"].chains
+    got = chains[chains[:, 0] == ai][:, 1:] if chains is not None else np.zeros((0, 9), np.int32)
+    want = GOLD[f"{name}/chains"]
+    want = np.stack([want[k] for k in want.dtype.names], axis=1) if len(want) else np.zeros((0, 9), np.int32)
+    assert np.array_equal(got, want)
+    anchors = env["res"].anchors
+    assert (0 if anchors is None else int((anchors[:, 0] == ai).sum())) == n_anchor
+
+
+def test_minimizer_count_matches_golden(env):
+    assert env["res"].counters["minimizers"] == sum(int(GOLD[f"{n}/meta"][1]) for n in env["names"])
+
+
+def test_batch_composition_does_not_change_results(env):
+    """Mapping an assembly alone == mapping it inside a batch (assemblies are independent units)."""
+    for name in ("mutated1", "mosaic_gene", "tiny_contigs"):
+        contigs = env["built"][name][1]
+        r1 = env["gi"].map_contigs([[s for _, s in contigs]])
+        check_against(r1, 0, GOLD[f"{name}/hits"], GOLD[f"{name}/cigar"])
+
+
+def test_scan_minimizers_equal_sequential_sketch(env):
+    name = "boundaries"
+    contigs = env["built"][name][1]
+    b = env["mapper"].AssemblyBatch.from_contigs([[s for _, s in contigs]])
+    h, c, p = env["gi"].scan_minimizers(b, 0, 200_000)
+    want = []
+    for ci, (_, s) in enumerate(contigs):
+        x, y = ol.sketch(s)
+        want += [(int(a >> 8), ci, int(bb)) for a, bb in zip(x, y)]
+    assert sorted(zip(h.tolist(), c.tolist(), p.tolist())) == sorted(want)
+
+
+def test_host_buffer_entry_point_equals_batch_path(env):
+    from kaptive_b200 import _lib
+
+    name = "mutated2"
+    seqs, off, ln = cases.flat_contigs(env["built"][name][1])
+    acs = np.array([0, len(ln)], dtype=np.int32)
+    h, arrays = env["mapper"].alloc_hits(4096)
+    cig = np.zeros(1 << 16, dtype=np.uint32)
+    nh, nc = C.c_int64(0), C.c_int64(0)
+    L = _lib.load()
+    _lib.check(L.kb_map_assemblies(env["gi"]._h, _lib.ptr(seqs), _lib.ptr(off), _lib.ptr(ln), _lib.ptr(acs), 1, C.byref(h), C.byref(nh),
+                                   _lib.ptr(cig), len(cig), C.byref(nc)))
+    g = GOLD[f"{name}/hits"]
+    assert nh.value == len(g)
+    for f in FIELDS:
+        assert np.array_equal(arrays[f][: nh.value].astype(np.int64), g[f].astype(np.int64)), f
+
+
+def test_index_image_roundtrip(env):
+    img = env["gi"].serialize()
+    gi2 = env["mapper"].GeneIndex.deserialize(img)
+    assert (gi2.n_genes, gi2.n_minimizers) == (env["gi"].n_genes, env["gi"].n_minimizers)
+    name = "two_loci"
+    r = gi2.map_contigs([[s for _, s in env["built"][name][1]]])
+    check_against(r, 0, GOLD[f"{name}/hits"], GOLD[f"{name}/cigar"])
+
+
+def test_capacity_and_argument_errors(env):
+    from kaptive_b200 import _lib
+
+    L = _lib.load()
+    seqs, off, ln = cases.flat_contigs(env["built"]["exact"][1])
+    acs = np.array([0, len(ln)], dtype=np.int32)
+    h, _ = env["mapper"].alloc_hits(1)
+    nh, nc = C.c_int64(0), C.c_int64(0)
+    rc = L.kb_map_assemblies(env["gi"]._h, _lib.ptr(seqs), _lib.ptr(off), _lib.ptr(ln), _lib.ptr(acs), 1, C.byref(h), C.byref(nh), None, 0, C.byref(nc))
+    assert rc == -4 and b"smaller" in L.kb_last_error()
+    assert nh.value == len(GOLD["exact/hits"])  # the size is still reported so the caller can retry
+
+
+def test_rammappy_shim_drop_in(env):
+    """The module the reference imports (serotyping/core.py:15-16): Index.build -> Aligner -> map_batch -> hit iterators."""
+    sys.path.insert(0, str(ROOT / "kaptive_b200" / "shim"))
+    import rammappy
+    from rammappy.align import Aligner
+
+    name = "clean_typeable"
+    db, contigs = env["built"][name]
+    recs = rammappy.fasta.parse_fasta_bytes(cases.fasta_bytes(contigs))
+    assert [(n, s) for n, s in recs] == [(n, s) for n, s in contigs]
+    index = rammappy.Index.build([(n.encode(), s) for n, s in recs])
+    aligner = Aligner(index=index, preset=None, do_cigar=True, do_cs=False, do_md=False)
+    opts = aligner.options
+    opts.filtering.best_n = 50000
+    opts.filtering.pri_ratio = 0.0
+    aligner.options = opts
+    queries = [(str(i).encode(), g) for i, g in enumerate(db.genes)]
+    its = aligner.map_batch(queries)
+    assert len(its) == len(queries)
+    g = GOLD[f"{name}/hits"]
+    k = 0
+    for qi, it in enumerate(its):
+        for h in it:
+            w = g[k]
+            assert w["gene"] == qi
+            assert h.target_name == contigs[w["t_ctg"]][0].encode()
+            assert (h.query_start, h.query_end, h.target_len, h.target_start, h.target_end) == (w["q_start"], w["q_end"], w["t_len"], w["t_start"], w["t_end"])
+            assert ("Forward" in repr(h.strand)) == (w["strand"] > 0)
+            assert (h.block_len, h.matches, h.edit_distance, h.score, h.mapq, h.is_primary) == (w["block_len"], w["matches"], w["edit_distance"], w["score"], w["mapq"], bool(w["is_primary"]))
+            cg = GOLD[f"{name}/cigar"][w["cigar_off"] : w["cigar_off"] + w["n_cigar"]]
+            assert h.cigar == ol.cigar_string(cg).encode()
+            k += 1
+    assert k == len(g)
+    # identical hits => the unmodified reference pipeline reports exactly this row (generated in the build container)
+    assert ROWS[name]["best_locus"] == "KL7" and ROWS[name]["typeable"] is True
+
+
+def test_full_size_assemblies_properties_and_oracle(env):
+    """BASELINE-size inputs (5 Mb assemblies, 150 x 20 gene db): oracle equality on two assemblies and
+    size-independent properties on all of them."""
+    from kaptive_b200 import synth
+
+    db = synth.make_db(n_loci=150, genes_per_locus=20, n_core=4, seed=1)
+    gi = env["mapper"].GeneIndex(db.genes)
+    asms = [synth.make_assembly(db, (7 * i) % 150, seed=1000 + i, genome_len=5_000_000) for i in range(6)]
+    res = gi.map_contigs([[s for _, s in a.contigs] for a in asms])
+    res2 = gi.map_contigs([[s for _, s in a.contigs] for a in asms])
+    for f in FIELDS:  # idempotence / determinism
+        assert np.array_equal(res.hits[f], res2.hits[f])
+    odb = ol.OracleDB(*db.flat())
+    for ai in (0, 3):
+        ro = odb.map(*asms[ai].flat())
+        check_against(res, ai, ro["hits"], ro["cigar"])
+    h = res.hits
+    lens = np.array([len(g) for g in db.genes])
+    assert np.all(h["q_start"] >= 0) and np.all(h["q_end"] <= lens[h["gene"]]) and np.all(h["q_start"] < h["q_end"])
+    assert np.all(h["t_start"] >= 0) and np.all(h["t_end"] <= h["t_len"]) and np.all(h["matches"] <= h["block_len"])
+    assert np.all(h["mapq"] <= 60)
+    for ai, a in enumerate(asms):  # hits arrive ordered by gene within an assembly
+        sel = h["asm_id"] == ai
+        assert np.all(np.diff(h["gene"][sel]) >= 0)
+        # every non-core gene of the embedded locus is found, almost end to end
+        mine = np.nonzero(db.gene_locus == a.locus)[0]
+        for g in mine[2:-2]:
+            cov = (h["q_end"] - h["q_start"])[sel & (h["gene"] == g)]
+            assert len(cov) and cov.sum() >= 0.6 * lens[g]
+    # CIGAR consistency: query / target spans
+    for i in range(0, len(res), 37):
+        cg = res.cigar_of(i)
+        ops, ln = cg & 0xF, cg >> 4
+        assert int(ln[(ops == 0) | (ops == 1)].sum()) == int(h["q_end"][i] - h["q_start"][i])
+        assert int(ln[(ops == 0) | (ops == 2)].sum()) == int(h["t_end"][i] - h["t_start"][i])
