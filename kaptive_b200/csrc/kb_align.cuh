@@ -114,17 +114,85 @@ KB_HD int32_t kb_gapcost2(const kb_params_t &P, int l)
     return c1 < c2 ? c1 : c2;
 }
 
+// the handful of scoring constants the DP inner loops need, passed by value so they live in registers
+struct KbDpConst {
+    int32_t a, b, q, e, q2, e2, sc_ambi, max_sw_cells;
+};
+KB_HD KbDpConst kb_dp_const(const kb_params_t &P)
+{
+    KbDpConst c;
+    c.a = P.a, c.b = P.b, c.q = P.q, c.e = P.e, c.q2 = P.q2, c.e2 = P.e2, c.sc_ambi = P.sc_ambi, c.max_sw_cells = P.max_sw_cells;
+    return c;
+}
+KB_HD int32_t kb_gapcost2(const KbDpConst &P, int l)
+{
+    int32_t c1 = P.q + P.e * l, c2 = P.q2 + P.e2 * l;
+    return c1 < c2 ? c1 : c2;
+}
+KB_HD int kb_sub_score(const KbDpConst &P, int ct, int cq)
+{
+    return (ct > 3 || cq > 3) ? -P.sc_ambi : (ct == cq ? P.a : -P.b);
+}
+
 KB_HD int kb_sub_score(const kb_params_t &P, int ct, int cq)
 {
     return (ct > 3 || cq > 3) ? -P.sc_ambi : (ct == cq ? P.a : -P.b);
 }
 
+// ksw_backtrack (is_rot) over the traceback bytes in S.tb; sequential, lane 0; result broadcast to the warp.
+template <int NL>
+KB_HD void kb_backtrack(int lane, int qlen, int tlen, int flag, KbEz &ez, const KbAlignScratch &S)
+{
+    const int32_t *off = S.off, *off_end = S.off + 2 * KB_DP_MAXLEN, *ppos = S.off + 4 * KB_DP_MAXLEN;
+    const uint8_t *p = S.tb;
+    int n_cigar = 0;
+    if (lane == 0) {
+        int i0 = -1, j0 = -1;
+        uint32_t *cg = S.ezcig;
+        if (!ez.zdropped && !(flag & KB_EZ_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
+        else if (ez.max_t >= 0 && ez.max_q >= 0) i0 = ez.max_t, j0 = ez.max_q;
+        if (i0 >= 0 && j0 >= 0) {
+            int i = i0, j = j0, state = 0;
+            auto push = [&](uint32_t op, int len) {
+                if (n_cigar == 0 || op != (cg[n_cigar - 1] & 0xf)) {
+                    if (n_cigar < KB_CIG_MAX) cg[n_cigar] = (uint32_t)len << 4 | op;
+                    ++n_cigar;
+                } else if (n_cigar <= KB_CIG_MAX) cg[n_cigar - 1] += (uint32_t)len << 4;
+            };
+            while (i >= 0 && j >= 0) {
+                int force_state = -1, r = i + j;
+                uint32_t tmp;
+                if (i < off[r]) force_state = 2;
+                if (i > off_end[r]) force_state = 1;
+                tmp = force_state < 0 ? p[ppos[r] + i - off[r]] : 0;
+                if (state == 0) state = tmp & 7;
+                else if (!(tmp >> (state + 2) & 1)) state = 0;
+                if (state == 0) state = tmp & 7;
+                if (force_state >= 0) state = force_state;
+                if (state == 0) push(0, 1), --i, --j;
+                else if (state == 1 || state == 3) push(2, 1), --i;
+                else push(1, 1), --j;
+            }
+            if (i >= 0) push(2, i + 1);
+            if (j >= 0) push(1, j + 1);
+            if (n_cigar > KB_CIG_MAX) n_cigar = -1;  // overflow: reported as an error on the hit
+            else if (!(flag & KB_EZ_REV_CIGAR))
+                for (int a = 0; a < n_cigar >> 1; ++a) {
+                    uint32_t tmp = cg[a];
+                    cg[a] = cg[n_cigar - 1 - a], cg[n_cigar - 1 - a] = tmp;
+                }
+        }
+    }
+    kb_sync<NL>();
+    ez.n_cigar = kb_bcast<NL>(n_cigar);
+}
+
 // Dual-affine DP, anti-diagonal order (ksw_extd2 recurrences; see oracle/kb_oracle.c:extd2 for the spec).
 template <int NL>
-KB_HD void kb_extd2(const kb_params_t &P, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts, int w,
-                    int zdrop, int flag, KbEz &ez, const KbAlignScratch &S, int64_t *cell_counter)
+KB_HD void kb_extd2(const KbDpConst P, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts, int w,
+                    int zdrop, int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
 {
-    const int right = !!(flag & KB_EZ_RIGHT);
+    const int rb = (flag & KB_EZ_RIGHT) ? 1 : 0;
     const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
     ez.max = 0, ez.max_q = ez.max_t = -1, ez.score = KB_NEG_INF, ez.zdropped = 0, ez.n_cigar = 0;
     if (qlen <= 0 || tlen <= 0) return;
@@ -180,28 +248,16 @@ KB_HD void kb_extd2(const kb_params_t &P, int lane, int qlen, const uint8_t *qs,
             b1 = (h_left - q > b1 ? h_left - q : b1) - e;
             b2 = (h_left - q2 > b2 ? h_left - q2 : b2) - e2;
             z = h_diag + kb_sub_score(P, ts[t], qs[j]);
-            d = 0;
-            if (!right) {
-                if (a1 > z) d = 1, z = a1;
-                if (b1 > z) d = 2, z = b1;
-                if (a2 > z) d = 3, z = a2;
-                if (b2 > z) d = 4, z = b2;
-                hq = z - q, hq2 = z - q2;
-                if (a1 > hq) d |= 0x08;
-                if (b1 > hq) d |= 0x10;
-                if (a2 > hq2) d |= 0x20;
-                if (b2 > hq2) d |= 0x40;
-            } else {
-                if (a1 >= z) d = 1, z = a1;
-                if (b1 >= z) d = 2, z = b1;
-                if (a2 >= z) d = 3, z = a2;
-                if (b2 >= z) d = 4, z = b2;
-                hq = z - q, hq2 = z - q2;
-                if (a1 >= hq) d |= 0x08;
-                if (b1 >= hq) d |= 0x10;
-                if (a2 >= hq2) d |= 0x20;
-                if (b2 >= hq2) d |= 0x40;
-            }
+            d = 0;  // (x >= y) == (x + 1 > y): rb = 1 gives the gap-preferring tie rule of KB_EZ_RIGHT
+            if (a1 + rb > z) d = 1, z = a1;
+            if (b1 + rb > z) d = 2, z = b1;
+            if (a2 + rb > z) d = 3, z = a2;
+            if (b2 + rb > z) d = 4, z = b2;
+            hq = z - q - rb, hq2 = z - q2 - rb;
+            if (a1 > hq) d |= 0x08;
+            if (b1 > hq) d |= 0x10;
+            if (a2 > hq2) d |= 0x20;
+            if (b2 > hq2) d |= 0x40;
             Hc[t] = z, e1c[t] = a1, e2c[t] = a2, f1c[t] = b1, f2c[t] = b2;
             pr[t] = d;
             if (z > max_H) max_H = z, max_t = t;  // lanes visit t in increasing order: first maximum = lowest t
@@ -226,47 +282,38 @@ KB_HD void kb_extd2(const kb_params_t &P, int lane, int qlen, const uint8_t *qs,
     }
     kb_sync<NL>();
     if (cell_counter && lane == 0) *cell_counter += tb_n;
-    // ---- ksw_backtrack (is_rot); sequential, lane 0
-    int n_cigar = 0;
-    if (lane == 0) {
-        int i0 = -1, j0 = -1;
-        uint32_t *cg = S.ezcig;
-        if (!ez.zdropped && !(flag & KB_EZ_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
-        else if (ez.max_t >= 0 && ez.max_q >= 0) i0 = ez.max_t, j0 = ez.max_q;
-        if (i0 >= 0 && j0 >= 0) {
-            int i = i0, j = j0, state = 0;
-            auto push = [&](uint32_t op, int len) {
-                if (n_cigar == 0 || op != (cg[n_cigar - 1] & 0xf)) {
-                    if (n_cigar < KB_CIG_MAX) cg[n_cigar] = (uint32_t)len << 4 | op;
-                    ++n_cigar;
-                } else if (n_cigar <= KB_CIG_MAX) cg[n_cigar - 1] += (uint32_t)len << 4;
-            };
-            while (i >= 0 && j >= 0) {
-                int force_state = -1, r = i + j;
-                uint32_t tmp;
-                if (i < off[r]) force_state = 2;
-                if (i > off_end[r]) force_state = 1;
-                tmp = force_state < 0 ? p[ppos[r] + i - off[r]] : 0;
-                if (state == 0) state = tmp & 7;
-                else if (!(tmp >> (state + 2) & 1)) state = 0;
-                if (state == 0) state = tmp & 7;
-                if (force_state >= 0) state = force_state;
-                if (state == 0) push(0, 1), --i, --j;
-                else if (state == 1 || state == 3) push(2, 1), --i;
-                else push(1, 1), --j;
-            }
-            if (i >= 0) push(2, i + 1);
-            if (j >= 0) push(1, j + 1);
-            if (n_cigar > KB_CIG_MAX) n_cigar = -1;  // overflow: reported as an error on the hit
-            else if (!(flag & KB_EZ_REV_CIGAR))
-                for (int a = 0; a < n_cigar >> 1; ++a) {
-                    uint32_t tmp = cg[a];
-                    cg[a] = cg[n_cigar - 1 - a], cg[n_cigar - 1 - a] = tmp;
-                }
-        }
+    kb_backtrack<NL>(lane, qlen, tlen, flag, ez, S);
+}
+
+#ifdef __CUDACC__
+#define kb_backtrack_lane0(lane, qlen, tlen, flag, ez, S) kb_backtrack<32>(lane, qlen, tlen, flag, ez, S)
+#include "kb_align_reg.cuh"
+// device-side choice between the register-resident DP and the scratch-memory DP (identical results)
+static __device__ __noinline__ void kb_dp_device(const KbDpConst P, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts,
+                                                 int w, int zdrop, int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
+{
+    const int width = qlen < tlen ? qlen : tlen;
+    // register paths need a band that never binds: every anti-diagonal is then a full slice of the rectangle
+    const bool fits = qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN &&
+                      w >= qlen + tlen;
+    if (fits && (width <= 32 * 7 || (flag & KB_EZ_GLOBAL_NO_ZDROP)))
+        kb_extd2_reg8(P, lane, qlen, qs, tlen, ts, zdrop, flag, width > 32 * 7, ez, S, cell_counter);
+    else kb_extd2<32>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+}
+#endif
+
+template <int NL>
+KB_HD void kb_dp(const kb_params_t &PP, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts, int w, int zdrop, int flag,
+                 KbEz &ez, const KbAlignScratch &S, int64_t *cell_counter)
+{
+    const KbDpConst P = kb_dp_const(PP);
+#ifdef __CUDA_ARCH__
+    if (NL == 32) {
+        kb_dp_device(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+        return;
     }
-    kb_sync<NL>();
-    ez.n_cigar = kb_bcast<NL>(n_cigar);
+#endif
+    kb_extd2<NL>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
 }
 
 // ---------------------------------------------------------------- mm_align1 pieces (all lanes run them redundantly)
@@ -685,7 +732,7 @@ KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int 
             for (int x = lane; x < tl; x += NL) S.tbuf[x] = tfull[rs - 1 - x];
         }
         kb_sync<NL>();
-        kb_extd2<NL>(P, lane, ql, S.qbuf, tl, S.tbuf, bw, P.zdrop, KB_EZ_EXTZ_ONLY | KB_EZ_RIGHT | KB_EZ_REV_CIGAR, ez, S, cell_counter);
+        kb_dp<NL>(P, lane, ql, S.qbuf, tl, S.tbuf, bw, P.zdrop, KB_EZ_EXTZ_ONLY | KB_EZ_RIGHT | KB_EZ_REV_CIGAR, ez, S, cell_counter);
         if (ez.n_cigar < 0) return 3;
         if (ez.n_cigar > 0) {
             if (lane == 0) kb_append_cigar(r, S.cigar, ez.n_cigar, S.ezcig);
@@ -706,11 +753,11 @@ KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int 
             int j, bw1 = bw_long, zdrop_code;
             const uint8_t *tseq = tfull + rs, *qseq = qseq0 + qs;
             if (ay[as1 + i] & KB_SEED_LONG_JOIN) bw1 = qe - qs > re - rs ? qe - qs : re - rs;
-            kb_extd2<NL>(P, lane, qe - qs, qseq, re - rs, tseq, bw1, -1, KB_EZ_GLOBAL_NO_ZDROP, ez, S, cell_counter);
+            kb_dp<NL>(P, lane, qe - qs, qseq, re - rs, tseq, bw1, -1, KB_EZ_GLOBAL_NO_ZDROP, ez, S, cell_counter);
             if (ez.n_cigar < 0) return 3;
             zdrop_code = ez.zdropped ? 1 : kb_test_zdrop(P, qseq, tseq, ez.n_cigar, S.ezcig);
             if (zdrop_code != 0) {
-                kb_extd2<NL>(P, lane, qe - qs, qseq, re - rs, tseq, bw1, P.zdrop, 0, ez, S, cell_counter);
+                kb_dp<NL>(P, lane, qe - qs, qseq, re - rs, tseq, bw1, P.zdrop, 0, ez, S, cell_counter);
                 if (ez.n_cigar < 0) return 3;
             }
             if (ez.n_cigar > 0) {
@@ -735,7 +782,7 @@ KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int 
     }
 
     if (!dropped && qe < qe0 && re < re0) {  // right extension
-        kb_extd2<NL>(P, lane, qe0 - qe, qseq0 + qe, re0 - re, tfull + re, bw, P.zdrop, KB_EZ_EXTZ_ONLY, ez, S, cell_counter);
+        kb_dp<NL>(P, lane, qe0 - qe, qseq0 + qe, re0 - re, tfull + re, bw, P.zdrop, KB_EZ_EXTZ_ONLY, ez, S, cell_counter);
         if (ez.n_cigar < 0) return 3;
         if (ez.n_cigar > 0) {
             if (lane == 0) kb_append_cigar(r, S.cigar, ez.n_cigar, S.ezcig);
