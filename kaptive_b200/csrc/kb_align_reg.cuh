@@ -19,6 +19,28 @@
 #pragma once
 #ifdef __CUDACC__
 
+// All DP operands live in global memory; say so, otherwise loads through pointers that crossed a call are generic.
+__device__ __forceinline__ int kb_ld_u8(const uint8_t *p)
+{
+    unsigned v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return (int)v;
+}
+__device__ __forceinline__ void kb_st_u8(uint8_t *p, int v)
+{
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t kb_ld_s32(const int32_t *p)
+{
+    int32_t v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ void kb_st_s32(int32_t *p, int32_t v)
+{
+    asm volatile("st.global.s32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+
 // number of cells on anti-diagonals 0..r-1 of a qlen x tlen rectangle
 __device__ __forceinline__ int kb_ppos_rect(int r, int qlen, int tlen)
 {
@@ -78,7 +100,7 @@ __device__ __forceinline__ void kb_backtrack_rect(int lane, int qlen, int tlen, 
         uint32_t tmp = 0xff;
         if (in) {
             const int r = ik + jk, st = r - qlen + 1 > 0 ? r - qlen + 1 : 0;
-            tmp = p[kb_ppos_rect(r, qlen, tlen) + ik - st];
+            tmp = (uint32_t)kb_ld_u8(p + kb_ppos_rect(r, qlen, tlen) + ik - st);
         }
         const uint32_t t0 = __shfl_sync(0xffffffffu, tmp, 0);
         // resolve the current cell exactly as ksw_backtrack does
@@ -160,24 +182,23 @@ static __device__ __noinline__ void kb_extd2_reg8(const KbDpConst P, int lane, i
                 const int t = (b << 5) + lane;
                 if (t >= st && t <= en) {
                     const int j = r - t;
-                    int32_t h_up, h_left, h_diag, a1, a2, b1, b2;
-                    if (t == 0) h_up = -kb_gapcost2(P, j + 1), a1 = a2 = KB_NEG_INF;
-                    else if (t == T0) h_up = ein[j], a1 = ein[KB_DP_MAXLEN + j], a2 = ein[2 * KB_DP_MAXLEN + j];  // previous tile's last column
-                    else h_up = upH, a1 = upE1, a2 = upE2;
-                    if (j == 0) h_left = -kb_gapcost2(P, t + 1), b1 = b2 = KB_NEG_INF;
-                    else h_left = H1[m], b1 = F1r[m], b2 = F2r[m];
-                    if (t == 0) h_diag = j == 0 ? 0 : -kb_gapcost2(P, j);
-                    else if (j == 0) h_diag = -kb_gapcost2(P, t);
-                    else if (t == T0) h_diag = ein[j - 1];
-                    else h_diag = HD[m];
+                    int32_t h_up = upH, a1 = upE1, a2 = upE2, h_left = H1[m], b1 = F1r[m], b2 = F2r[m], h_diag = HD[m];
+                    if (t == 0 || j == 0 || t == T0) {  // rectangle / tile edges: a handful of lanes per anti-diagonal
+                        if (t == 0) h_up = -kb_gapcost2(P, j + 1), a1 = a2 = KB_NEG_INF;
+                        else if (t == T0) h_up = kb_ld_s32(ein + j), a1 = kb_ld_s32(ein + KB_DP_MAXLEN + j), a2 = kb_ld_s32(ein + 2 * KB_DP_MAXLEN + j);
+                        if (j == 0) h_left = -kb_gapcost2(P, t + 1), b1 = b2 = KB_NEG_INF;
+                        if (t == 0) h_diag = j == 0 ? 0 : -kb_gapcost2(P, j);
+                        else if (j == 0) h_diag = -kb_gapcost2(P, t);
+                        else if (t == T0) h_diag = kb_ld_s32(ein + j - 1);
+                    }
                     int d;
-                    const int32_t z = kb_cell(P, rb, h_up, a1, a2, h_left, b1, b2, h_diag, ts[t], qs[j], E1r[m], E2r[m], F1r[m], F2r[m], d);
+                    const int32_t z = kb_cell(P, rb, h_up, a1, a2, h_left, b1, b2, h_diag, kb_ld_u8(ts + t), kb_ld_u8(qs + j), E1r[m], E2r[m], F1r[m], F2r[m], d);
                     HD[m] = upH;  // H(t-1, j): the diagonal neighbour of (t, j+1) on the next anti-diagonal
                     H1[m] = z;
-                    pr[t] = (uint8_t)d;
+                    kb_st_u8(pr + t, d);
                     if (z > max_H || (z == max_H && t < max_t)) max_H = z, max_t = t;
                     if (t == T1 - 1) {  // last column: spill it for the next tile; the last one ends with H(tlen-1, qlen-1)
-                        if (tiled) eout[j] = z, eout[KB_DP_MAXLEN + j] = E1r[m], eout[2 * KB_DP_MAXLEN + j] = E2r[m];
+                        if (tiled) kb_st_s32(eout + j, z), kb_st_s32(eout + KB_DP_MAXLEN + j, E1r[m]), kb_st_s32(eout + 2 * KB_DP_MAXLEN + j, E2r[m]);
                         last_h = z;
                     }
                 }

@@ -166,7 +166,10 @@ void kb_launch_chain(const KbIndexView &ix, const KbBatchView &bt, const uint64_
 }
 
 // ------------------------------------------------------------------ alignment: one warp per chain, persistent
-__global__ void __launch_bounds__(128) kb_align_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
+#ifndef KB_ALIGN_MINB
+#define KB_ALIGN_MINB 3
+#endif
+__global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
                                                        const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, uint8_t *scratch,
                                                        size_t scratch_bytes, KbRawHit *raw, int64_t raw_cap, uint32_t *pool,
                                                        int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain)

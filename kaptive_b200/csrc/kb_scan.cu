@@ -67,6 +67,30 @@ struct LaneFetch {
     }
 };
 
+// W sketch steps (compile-time window slots) with the ballot-based queue push between them.
+template <int W, int K, int U, class Slow>
+struct KbScanUnroll {
+    __device__ __forceinline__ static void run(KbFastSketch<W, K> &s, int i0, int i_end, int live_from, const LaneFetch &F, Slow &slow,
+                                               ScanQueue &Q, int &front, int lane)
+    {
+        const int i = i0 + U;
+        uint32_t ex = 0, ey = 0;
+        bool e = false;
+        if (i < i_end) e = kb_fast_step<W, K, U>(s, i, F(i), i >= live_from, &ex, &ey, slow);
+        const unsigned bal = __ballot_sync(0xffffffffu, e);
+        if (e) {
+            const int o = front + __popc(bal & ((1u << lane) - 1u));
+            Q.x[o] = ex, Q.y[o] = ey;
+        }
+        front += __popc(bal);
+        KbScanUnroll<W, K, U + 1, Slow>::run(s, i0, i_end, live_from, F, slow, Q, front, lane);
+    }
+};
+template <int W, int K, class Slow>
+struct KbScanUnroll<W, K, W, Slow> {
+    __device__ __forceinline__ static void run(KbFastSketch<W, K> &, int, int, int, const LaneFetch &, Slow &, ScanQueue &, int &, int) {}
+};
+
 template <int W, int K>
 __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
                                                       unsigned long long *counters, int64_t anchor_cap,
@@ -132,35 +156,40 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
         }
         __syncwarp();
 
-        // ---- sketch: all lanes step together so the queue can be drained at converged points
-        KbSketchState<W, K> s;
+        // ---- sketch: all lanes step together; at most one regular minimizer per lane and step goes to the front of
+        // the queue through a ballot (no atomics); the rare identical-k-mer emissions of mm_sketch go to the back of
+        // the queue through a shared-memory counter.  The queue is drained whenever it holds >= 32 entries.
+        KbFastSketch<W, K> s;
         s.reset();
         const bool active = lstart < lend;
         const int p0pos = lstart >= KB_SCAN_LOOKBACK ? lstart - KB_SCAN_LOOKBACK : 0;
-        auto emit = [&](uint32_t x, uint32_t y) {
-            int slot = atomicAdd(&tail, 1);
-            if (slot < KB_QCAP) Q.x[slot] = x, Q.y[slot] = y;
+        int front = 0;  // warp-uniform: entries pushed at the front of the queue
+        auto slow = [&](uint32_t x, uint32_t y) {
+            int k = atomicAdd(&tail, 1);  // `tail` counts the slow entries, stored from the back
+            if (front + k < KB_QCAP - 64) Q.x[KB_QCAP - 1 - k] = x, Q.y[KB_QCAP - 1 - k] = y;
+            else atomicOr(&counters[6], 1ull);
         };
         const int n_iter = (KB_LANE_BASES + KB_SCAN_LOOKBACK + W - 1) / W;
         for (int it = 0; it <= n_iter; ++it) {
             if (it < n_iter) {
-                if (active) {
-                    int i0 = p0pos + it * W;
-                    KbSketchUnroll<W, K, 0, decltype(emit), LaneFetch>::run(s, i0, lend, lstart, F, emit);
-                }
-            } else if (active && lend == clen && s.min_x != KB_MAXU) emit(s.min_x, s.min_y);  // mm_sketch's final push
-            __syncwarp();
-            int n = tail;
-            if (n > KB_QCAP) {  // cannot happen for DNA (<= ~1 push per base); flag it rather than corrupt memory
-                if (lane == 0) atomicOr(&counters[6], 1ull);
-                n = KB_QCAP;
+                const int i0 = p0pos + it * W;
+                KbScanUnroll<W, K, 0, decltype(slow)>::run(s, i0, active ? lend : 0, lstart, F, slow, Q, front, lane);
+            } else {  // mm_sketch's final push, by the lane that owns the end of the contig
+                const bool e = active && lend == clen && s.mx != KB_MAXU;
+                const unsigned bal = __ballot_sync(0xffffffffu, e);
+                if (e) Q.x[front] = s.mx, Q.y[front] = s.my;  // at most one lane
+                front += __popc(bal);
             }
-            if (n >= 32 || (it == n_iter && n > 0)) {
+            __syncwarp();
+            const int n_slow = tail;
+            if (front + n_slow >= 32 || (it == n_iter && front + n_slow > 0)) {
+                const int n = front + n_slow;
                 n_min_local += (lane == 0) ? (unsigned long long)n : 0ull;
                 for (int base = 0; base < n; base += 32) {
                     int qi = base + lane;
                     bool have = qi < n;
-                    uint32_t hx = have ? Q.x[qi] : 0, hy = have ? Q.y[qi] : 0;
+                    int qslot = qi < front ? qi : KB_QCAP - 1 - (qi - front);
+                    uint32_t hx = have ? Q.x[qslot] : 0, hy = have ? Q.y[qslot] : 0;
                     uint32_t est = 0, ecnt = 0;
                     bool hit = have && kb_ht_lookup(ix.ht, ix.ht_mask, hx, &est, &ecnt);
                     if (mz_hash && have && asm_id == mz_asm) {  // debug / parity dump of one assembly's minimizers
@@ -202,6 +231,7 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
                     }
                 }
                 __syncwarp();
+                front = 0;
                 if (lane == 0) tail = 0;
                 __syncwarp();
             }

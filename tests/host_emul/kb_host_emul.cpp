@@ -102,7 +102,9 @@ EmuResult *kbe_map_assembly(void *idx_, const uint8_t *ascii, const int64_t *ctg
     std::vector<uint32_t> aval;
     std::vector<uint16_t> occ((size_t)ix.n_entries, 0);
     std::vector<uint32_t> all_hash;
-    if (lane_bases <= 0) lane_bases = KB_LANE_BASES;
+    const bool fast = lane_bases < 0;  // negative slice size: run the branch-free sketch the scan kernel uses
+    if (fast) lane_bases = -lane_bases;
+    if (lane_bases == 0) lane_bases = KB_LANE_BASES;
     for (int c = 0; c < n_ctg; ++c) {
         PackedFetch fetch{bt.seq2, bt.nmask, bt.ctg_soff[c]};
         for (int s = 0; s < ctg_len[c]; s += lane_bases) {
@@ -121,7 +123,8 @@ EmuResult *kbe_map_assembly(void *idx_, const uint8_t *ascii, const int64_t *ctg
                     if (occ[st + j] < 0xffff) ++occ[st + j];
                 }
             };
-            kb_sketch_slice<10, 15>(ctg_len[c], s, e, fetch, emit);
+            if (fast) kb_fast_slice<10, 15>(ctg_len[c], s, e, fetch, emit);
+            else kb_sketch_slice<10, 15>(ctg_len[c], s, e, fetch, emit);
         }
     }
     R->n_minimizers = (int64_t)all_hash.size();

@@ -38,10 +38,11 @@ def test_emulation_matches_golden(name):
     assert [r["mid_occ"], r["n_minimizers"], len(r["anchors"])] == list(GOLD[f"{name}/meta"])
 
 
-@pytest.mark.parametrize("lane_bases", [1, 7, 24, 25, 64, 1000])
+@pytest.mark.parametrize("lane_bases", [1, 7, 24, 25, 64, 1000, -1, -9, -10, -11, -256, -100000])
 def test_scan_slicing_is_exact(lane_bases):
-    """Sketching independent slices with a w+k-1 look-back gives exactly the sequential minimizer list."""
-    for name in ("n_rich", "tiny_contigs", "boundaries"):
+    """Sketching independent slices with a w+k-1 look-back gives exactly the sequential minimizer list
+    (negative sizes: the branch-free sliding-window sketch the scan kernel runs)."""
+    for name in ("n_rich", "tiny_contigs", "boundaries", "repeat_gene"):
         db, contigs = cases.CASES[name]()
         flat = cases.flat_contigs(contigs)
         r = emul_index(db).map(*flat, lane_bases=lane_bases, keep_stages=True)
@@ -83,3 +84,25 @@ def test_random_cases_against_oracle():
         ro = odb.map(*a.flat(), keep_stages=True)
         re = edb.map(*a.flat(), lane_bases=(256, 100, 33)[s % 3], keep_stages=True)
         assert_same(re, ro["hits"], ro["cigar"], ro["chains"])
+
+
+def test_fast_sketch_on_low_complexity_sequence():
+    """Homopolymers, short tandem repeats and N runs: the identical-k-mer paths of mm_sketch."""
+    import numpy as np
+
+    rng = np.random.default_rng(4)
+    parts = [b"A" * 300, b"AT" * 200, b"ACG" * 150, b"N" * 40, b"ACGTTGCA" * 60, b"AAAAAAAAAAAAAAAC" * 30, b"N", b"GATTACA" * 90]
+    for _ in range(10):
+        parts.append(bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=int(rng.integers(1, 400)), p=[.24, .24, .24, .24, .04])))
+        parts.append(bytes(rng.choice(np.frombuffer(b"AC", np.uint8), size=int(rng.integers(1, 200)))))
+    seq = b"".join(parts)
+    db = cases.small_db()
+    contigs = [("lc", seq), ("lc2", seq[::-1]), ("h", b"C" * 5000)]
+    flat = cases.flat_contigs(contigs)
+    want = []
+    for ci, (_, s) in enumerate(contigs):
+        x, y = ol.sketch(s)
+        want += [(int(a >> 8), ci, int(b)) for a, b in zip(x, y)]
+    for lb in (-256, -17, 256):
+        r = emul_index(db).map(*flat, lane_bases=lb, keep_stages=True)
+        assert sorted(zip(r["mz_hash"].tolist(), r["mz_ctg"].tolist(), r["mz_pos"].tolist())) == sorted(want), lb
