@@ -147,6 +147,22 @@ int kb_scan_minimizers(const kb_index_t *idx, const kb_batch_t *batch, int32_t a
 /* times `iters` launches of the seeding scan kernel alone; returns mean ms */
 int kb_bench_scan(const kb_index_t *idx, const kb_batch_t *batch, int iters, float *mean_ms, int64_t *n_anchors);
 
+/* ---- post-mapping numerics, batched over all items of a batch of assemblies ----
+ * Host or device pointers in, host arrays out; bit-exact replacements of the reference's numba kernels. */
+const char *kb_post_last_error(void);
+/* _extract_ragged_kernel (src/kaptive/core/seq.py:612-668): slices [starts, ends) of parent sequences, reverse-
+ * complemented where strands < 0.  out_off / out_len: n entries. */
+int kb_post_extract(const uint8_t *seqs, int64_t n_seq_bytes, const int64_t *parent_off, int32_t n_parents, const int32_t *indices,
+                    const int32_t *starts, const int32_t *ends, const int8_t *strands, int32_t n, uint8_t *out, int64_t out_cap,
+                    int64_t *out_off, int32_t *out_len);
+/* _translate_ragged_kernel (src/kaptive/core/seq.py:671-741): table 11, per-item frame, optional stop at first '*'. */
+int kb_post_translate(const uint8_t *seqs, int64_t n_seq_bytes, const int64_t *offsets, const int32_t *lengths, const int8_t *frames,
+                      int32_t n, int32_t to_stop, uint8_t *out, int64_t out_cap, int64_t *out_off, int32_t *out_len, int64_t *n_out);
+/* _batched_banded_gotoh (src/kaptive/core/pairwise.py:395-584), unseeded: banded local Gotoh on BLOSUM62 with traceback.
+ * res: n x 8 int32 = score, matches, mismatches, gaps, q_start, q_end, t_start, t_end. */
+int kb_post_protein_align(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t, const int64_t *t_off,
+                          const int32_t *t_len, int32_t n, int32_t k, int32_t gap_open, int32_t gap_extend, int32_t *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,10 @@ _SYMBOLS = [
     ("kb_map_assemblies", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(KbHits), _P, _P, C.c_int64, _P]),
     ("kb_scan_minimizers", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     ("kb_bench_scan", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("kb_post_last_error", C.c_char_p, []),
+    ("kb_post_extract", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int64, _P, _P]),
+    ("kb_post_translate", C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]),
+    ("kb_post_protein_align", C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 ]  # fmt: skip
 
 _lib = None

@@ -1,0 +1,346 @@
+// kb_post.cu -- post-mapping numerics of the typing path on the GPU (first "next" row).
+//
+//   kb_post_extract        replaces _extract_ragged_kernel   (src/kaptive/core/seq.py:612-668; called serotyping/core.py:333,352)
+//   kb_post_translate      replaces _translate_ragged_kernel (src/kaptive/core/seq.py:671-741; called serotyping/core.py:360)
+//   kb_post_protein_align  replaces _batched_banded_gotoh    (src/kaptive/core/pairwise.py:395-584; called serotyping/core.py:378)
+//
+// The reference launches each of these once per assembly on ~20-60 items, which costs it ~6 ms of numba parallel-region
+// wake-up per call; here one call handles the items of a whole batch of assemblies.  Bit-exact: integer/byte work only.
+// Byte gathers are one thread per output byte (coalesced writes); the protein DP is one thread per pair with the two
+// live rows and a 1-byte/cell packed traceback in global scratch -- thousands of independent pairs per call are the
+// parallelism, exactly as in the reference's prange.
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "kb_common.cuh"
+#include "kb_post_tables.h"
+
+namespace {
+thread_local std::string g_post_err;
+
+struct PostTables {
+    uint8_t comp[256], chr[256], codon[128];
+    int8_t aa_idx[256];  // index into the 25-letter alphabet or -1
+    int8_t blosum[25 * 25];
+};
+__constant__ PostTables c_tab;
+bool g_tables_uploaded[64] = {false};
+
+void build_tables(PostTables &T)
+{
+    const char *from = "ACGTUacgtu", *to = "TGCAAtgcaa", *ord = "TCAG", *alpha = KB_AA_ALPHABET;
+    for (int i = 0; i < 256; ++i) T.comp[i] = (uint8_t)i, T.chr[i] = 4, T.aa_idx[i] = -1;
+    for (int i = 0; from[i]; ++i) T.comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    for (int i = 0; i < 4; ++i) T.chr[(uint8_t)"ACGT"[i]] = (uint8_t)i, T.chr[(uint8_t)"acgt"[i]] = (uint8_t)i;
+    T.chr['U'] = T.chr['u'] = 3;
+    for (int i = 0; i < 128; ++i) T.codon[i] = 'X';
+    int idx[256] = {0}, k = 0;
+    idx['A'] = 0, idx['C'] = 1, idx['G'] = 2, idx['T'] = 3;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+            for (int c = 0; c < 4; ++c) T.codon[idx[(int)ord[a]] * 25 + idx[(int)ord[b]] * 5 + idx[(int)ord[c]]] = (uint8_t)KB_CODE_TCAG[k++];
+    for (int a = 0; a < 25; ++a) T.aa_idx[(uint8_t)alpha[a]] = (int8_t)a;
+    for (int i = 0; i < 625; ++i) T.blosum[i] = KB_BLOSUM62[i];
+}
+
+#define PCU(x)                                                                              \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) {                                                            \
+            g_post_err = std::string(#x) + " failed: " + cudaGetErrorString(e_);            \
+            throw g_post_err;                                                               \
+        }                                                                                   \
+    } while (0)
+
+struct Dev {  // tiny RAII helper: device buffers freed on scope exit
+    std::vector<void *> p;
+    template <class T>
+    T *alloc(size_t n)
+    {
+        void *q = nullptr;
+        PCU(cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+        p.push_back(q);
+        return (T *)q;
+    }
+    template <class T>
+    T *upload(const T *h, size_t n)
+    {
+        T *d = alloc<T>(n);
+        if (n) PCU(cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyDefault));
+        return d;
+    }
+    ~Dev()
+    {
+        for (void *q : p) cudaFree(q);
+    }
+};
+
+void ensure_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        g_post_err = "no CUDA device: libkaptive_b200 has no CPU fallback";
+        throw g_post_err;
+    }
+    int dev = 0;
+    PCU(cudaGetDevice(&dev));
+    if (dev < 64 && !g_tables_uploaded[dev]) {
+        PostTables T;
+        build_tables(T);
+        PCU(cudaMemcpyToSymbol(c_tab, &T, sizeof(T)));
+        g_tables_uploaded[dev] = true;
+    }
+}
+
+// ---- extract: item i = bytes [starts[i], ends[i]) of parent indices[i], reverse-complemented when strands[i] < 0
+__global__ void extract_kernel(const uint8_t *seqs, const int64_t *poff, const int32_t *indices, const int32_t *starts, const int32_t *ends,
+                               const int8_t *strands, const int64_t *out_off, int32_t n, int64_t total, uint8_t *out)
+{
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;  // last item whose output starts at or before o and is not empty before o
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (out_off[mid] <= o) lo = mid;
+            else hi = mid - 1;
+        }
+        const int i = lo;
+        const int64_t c = o - out_off[i];
+        const int64_t base = poff[indices[i]];
+        out[o] = strands[i] >= 0 ? seqs[base + starts[i] + c] : c_tab.comp[seqs[base + ends[i] - 1 - c]];
+    }
+}
+
+// ---- translate, pass 1: number of codons before the first stop (to_stop) per item; one thread per item
+__global__ void translate_count_kernel(const uint8_t *seqs, const int64_t *off, const int32_t *len, const int8_t *frames, int32_t n,
+                                       int to_stop, int32_t *out_len)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t L = len[i], f = frames[i], nc = 0;
+    if (L > f) {
+        int32_t adj = L - f, mx = adj >= 3 ? adj / 3 : 0;
+        if (!to_stop) nc = mx;
+        else {
+            const uint8_t *p = seqs + off[i] + f;
+            for (; nc < mx; ++nc, p += 3)
+                if (c_tab.codon[c_tab.chr[p[0]] * 25 + c_tab.chr[p[1]] * 5 + c_tab.chr[p[2]]] == 42) break;
+        }
+    }
+    out_len[i] = nc;
+}
+// pass 2: one thread per output residue
+__global__ void translate_fill_kernel(const uint8_t *seqs, const int64_t *off, const int8_t *frames, const int64_t *out_off, int32_t n,
+                                      int64_t total, uint8_t *out)
+{
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (out_off[mid] <= o) lo = mid;
+            else hi = mid - 1;
+        }
+        const uint8_t *p = seqs + off[lo] + frames[lo] + 3 * (o - out_off[lo]);
+        out[o] = c_tab.codon[c_tab.chr[p[0]] * 25 + c_tab.chr[p[1]] * 5 + c_tab.chr[p[2]]];
+    }
+}
+
+// ---- banded local Gotoh with traceback, one thread per pair (the reference's loop body, rolling rows)
+// traceback byte: bits 0-1 tb_M (0 diag, 1 D, 2 I, 3 stop), bit 2 tb_D extended, bit 3 tb_I extended
+__global__ void gotoh_kernel(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t, const int64_t *t_off,
+                             const int32_t *t_len, int32_t n, int32_t k, int32_t go, int32_t ge, const int64_t *tb_off, uint8_t *tb,
+                             const int64_t *row_off, int32_t *rowbuf, int32_t *res)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int32_t INF = -1000000000;
+    const uint8_t *s1 = q + q_off[idx], *s2 = t + t_off[idx];
+    const int32_t len1 = q_len[idx], len2 = t_len[idx], rows = len1 + 1, cols = len2 + 1;
+    const int32_t dl = len1 > len2 ? len1 - len2 : len2 - len1;
+    const int32_t kl = k > dl + 1 ? k : dl + 1, bw = 2 * kl + 3;
+    uint8_t *T = tb + tb_off[idx];
+    int32_t *Mp = rowbuf + row_off[idx], *Dp = Mp + bw, *Mc = Dp + bw, *Dc = Mc + bw;  // previous / current rows of M and D
+    int32_t max_score = 0, max_i = 0, max_j = 0;
+    // row 0: every in-range cell is the initial state (M = 0, D = -inf, stop)
+    for (int32_t jm = 0; jm < bw; ++jm) Mp[jm] = 0, Dp[jm] = INF;
+    for (int32_t i = 1; i < rows; ++i) {
+        const int32_t sj = i - kl > 1 ? i - kl : 1, ej = i + kl + 1 < cols ? i + kl + 1 : cols;
+        const int32_t sp = i - 1 - kl - 1 > 0 ? i - 1 - kl - 1 : 0, sc = i - kl - 1 > 0 ? i - kl - 1 : 0;
+        // cells of the previous row that were initialised but not computed read as the initial state; the same for this row
+        for (int32_t jm = 0; jm < bw; ++jm) Mc[jm] = 0, Dc[jm] = INF;
+        if (sj < cols && ej > 1) {
+            const int32_t ai = c_tab.aa_idx[s1[i - 1]];
+            int32_t m_left = 0, i_left = INF;  // (i, sj - 1) is an initialised, never computed cell
+            // the previous row was computed for columns [psj, pej); outside of it the initial state applies
+            const int32_t psj = i - 1 >= 1 ? (i - 1 - kl > 1 ? i - 1 - kl : 1) : cols, pej = i - 1 >= 1 ? (i + kl < cols ? i + kl : cols) : 0;
+            for (int32_t j = sj; j < ej; ++j) {
+                const bool top_ok = j >= psj && j < pej, tl_ok = j - 1 >= psj && j - 1 < pej;
+                const int32_t m_top = top_ok ? Mp[j - sp] : 0, d_top = top_ok ? Dp[j - sp] : INF, m_tl = tl_ok ? Mp[j - 1 - sp] : 0;
+                const int32_t d_open = m_top - go - ge, d_ext = d_top - ge;
+                int32_t dcur, icur, tbv = 0;
+                if (d_open >= d_ext) dcur = d_open;
+                else dcur = d_ext, tbv |= 4;
+                const int32_t i_open = m_left - go - ge, i_ext = i_left - ge;
+                if (i_open >= i_ext) icur = i_open;
+                else icur = i_ext, tbv |= 8;
+                const int32_t bi = c_tab.aa_idx[s2[j - 1]];
+                const int32_t sub = (ai >= 0 && bi >= 0) ? (int32_t)c_tab.blosum[ai * 25 + bi] : -128;
+                int32_t best = m_tl + sub, tbm = 0;
+                if (dcur > best) best = dcur, tbm = 1;
+                if (icur > best) best = icur, tbm = 2;
+                int32_t mcur;
+                if (best <= 0) mcur = 0, tbm = 3;
+                else {
+                    mcur = best;
+                    if (best > max_score) max_score = best, max_i = i, max_j = j;
+                }
+                Mc[j - sc] = mcur, Dc[j - sc] = dcur;
+                T[(int64_t)i * bw + (j - sc)] = (uint8_t)(tbv | tbm);
+                m_left = mcur, i_left = icur;
+            }
+        }
+        int32_t *x = Mp;
+        Mp = Mc, Mc = x, x = Dp, Dp = Dc, Dc = x;
+    }
+    int32_t i = max_i, j = max_j, matches = 0, mismatches = 0, gaps = 0, state = 0;
+    while (i > 0 && j > 0) {
+        const int32_t sj = i - kl > 1 ? i - kl : 1, ej = i + kl + 1 < cols ? i + kl + 1 : cols;
+        const int32_t sc = i - kl - 1 > 0 ? i - kl - 1 : 0;
+        // a cell that was never computed keeps the initial traceback state: stop
+        const int32_t v = (j >= sj && j < ej) ? T[(int64_t)i * bw + (j - sc)] : 3;
+        if (state == 0) {
+            const int32_t tbm = v & 3;
+            if (tbm == 3) break;
+            else if (tbm == 0) {
+                if (s1[i - 1] == s2[j - 1]) ++matches;
+                else ++mismatches;
+                --i, --j;
+            } else state = tbm;
+        } else if (state == 1) {
+            ++gaps, --i;
+            if (!(v & 4)) state = 0;
+        } else {
+            ++gaps, --j;
+            if (!(v & 8)) state = 0;
+        }
+    }
+    int32_t *r = res + (int64_t)idx * 8;
+    r[0] = max_score, r[1] = matches, r[2] = mismatches, r[3] = gaps, r[4] = i, r[5] = max_i, r[6] = j, r[7] = max_j;
+}
+}  // namespace
+
+extern "C" {
+
+const char *kb_post_last_error(void) { return g_post_err.c_str(); }
+
+int kb_post_extract(const uint8_t *seqs, int64_t n_seq_bytes, const int64_t *parent_off, int32_t n_parents, const int32_t *indices,
+                    const int32_t *starts, const int32_t *ends, const int8_t *strands, int32_t n, uint8_t *out, int64_t out_cap,
+                    int64_t *out_off, int32_t *out_len)
+{
+    if (n < 0 || (n > 0 && (!seqs || !parent_off || !indices || !starts || !ends || !strands || !out_off || !out_len))) return KB_ERR_ARG;
+    try {
+        ensure_device();
+        int64_t total = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            int32_t L = ends[i] - starts[i];
+            if (L < 0 || indices[i] < 0 || indices[i] >= n_parents) {
+                g_post_err = "extract: bad interval";
+                return KB_ERR_ARG;
+            }
+            out_off[i] = total, out_len[i] = L, total += L;
+        }
+        if (total > out_cap) {
+            g_post_err = "extract: output buffer too small";
+            return KB_ERR_CAPACITY;
+        }
+        if (total == 0) return KB_OK;
+        Dev D;
+        const uint8_t *d_seq = D.upload(seqs, (size_t)n_seq_bytes);
+        const int64_t *d_poff = D.upload(parent_off, (size_t)n_parents);
+        const int32_t *d_idx = D.upload(indices, (size_t)n), *d_st = D.upload(starts, (size_t)n), *d_en = D.upload(ends, (size_t)n);
+        const int8_t *d_sd = D.upload(strands, (size_t)n);
+        const int64_t *d_oo = D.upload(out_off, (size_t)n);
+        uint8_t *d_out = D.alloc<uint8_t>((size_t)total);
+        int64_t grid = (total + 255) / 256;
+        if (grid > 148 * 16) grid = 148 * 16;
+        extract_kernel<<<(unsigned)grid, 256>>>(d_seq, d_poff, d_idx, d_st, d_en, d_sd, d_oo, n, total, d_out);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(out, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+int kb_post_translate(const uint8_t *seqs, int64_t n_seq_bytes, const int64_t *offsets, const int32_t *lengths, const int8_t *frames,
+                      int32_t n, int32_t to_stop, uint8_t *out, int64_t out_cap, int64_t *out_off, int32_t *out_len, int64_t *n_out)
+{
+    if (n < 0 || (n > 0 && (!seqs || !offsets || !lengths || !frames || !out_off || !out_len)) || !n_out) return KB_ERR_ARG;
+    *n_out = 0;
+    if (n == 0) return KB_OK;
+    try {
+        ensure_device();
+        Dev D;
+        const uint8_t *d_seq = D.upload(seqs, (size_t)n_seq_bytes);
+        const int64_t *d_off = D.upload(offsets, (size_t)n);
+        const int32_t *d_len = D.upload(lengths, (size_t)n);
+        const int8_t *d_fr = D.upload(frames, (size_t)n);
+        int32_t *d_olen = D.alloc<int32_t>((size_t)n);
+        translate_count_kernel<<<(n + 127) / 128, 128>>>(d_seq, d_off, d_len, d_fr, n, to_stop, d_olen);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        int64_t total = 0;
+        for (int32_t i = 0; i < n; ++i) out_off[i] = total, total += out_len[i];
+        *n_out = total;
+        if (total > out_cap) {
+            g_post_err = "translate: output buffer too small";
+            return KB_ERR_CAPACITY;
+        }
+        if (total == 0) return KB_OK;
+        const int64_t *d_oo = D.upload(out_off, (size_t)n);
+        uint8_t *d_out = D.alloc<uint8_t>((size_t)total);
+        int64_t grid = (total + 255) / 256;
+        if (grid > 148 * 16) grid = 148 * 16;
+        translate_fill_kernel<<<(unsigned)grid, 256>>>(d_seq, d_off, d_fr, d_oo, n, total, d_out);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(out, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+int kb_post_protein_align(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t, const int64_t *t_off,
+                          const int32_t *t_len, int32_t n, int32_t k, int32_t gap_open, int32_t gap_extend, int32_t *res)
+{
+    if (n < 0 || (n > 0 && (!q_off || !q_len || !t_off || !t_len || !res))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    try {
+        ensure_device();
+        std::vector<int64_t> tb_off((size_t)n), row_off((size_t)n);
+        int64_t tb_total = 0, row_total = 0, qb = 0, tbytes = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            if (q_len[i] < 0 || t_len[i] < 0) return KB_ERR_ARG;
+            int64_t dl = q_len[i] > t_len[i] ? q_len[i] - t_len[i] : t_len[i] - q_len[i];
+            int64_t kl = k > dl + 1 ? k : dl + 1, bw = 2 * kl + 3;
+            tb_off[(size_t)i] = tb_total, tb_total += ((int64_t)q_len[i] + 1) * bw;
+            row_off[(size_t)i] = row_total, row_total += 4 * bw;
+            qb = qb > q_off[i] + q_len[i] ? qb : q_off[i] + q_len[i];
+            tbytes = tbytes > t_off[i] + t_len[i] ? tbytes : t_off[i] + t_len[i];
+        }
+        Dev D;
+        const uint8_t *d_q = D.upload(q, (size_t)qb), *d_t = D.upload(t, (size_t)tbytes);
+        const int64_t *d_qo = D.upload(q_off, (size_t)n), *d_to = D.upload(t_off, (size_t)n);
+        const int32_t *d_ql = D.upload(q_len, (size_t)n), *d_tl = D.upload(t_len, (size_t)n);
+        const int64_t *d_tbo = D.upload(tb_off.data(), (size_t)n), *d_ro = D.upload(row_off.data(), (size_t)n);
+        uint8_t *d_tb = D.alloc<uint8_t>((size_t)tb_total);
+        int32_t *d_rows = D.alloc<int32_t>((size_t)row_total), *d_res = D.alloc<int32_t>((size_t)n * 8);
+        gotoh_kernel<<<(n + 63) / 64, 64>>>(d_q, d_qo, d_ql, d_t, d_to, d_tl, n, k, gap_open, gap_extend, d_tbo, d_tb, d_ro, d_rows, d_res);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(res, d_res, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+}  // extern "C"
