@@ -167,6 +167,8 @@ static __device__ __noinline__ void kb_extd2_reg8(const KbDpConst P, int lane, i
             int32_t max_H = INT32_MIN, max_t = 0x7fffffff;
             // slot M-1 is overwritten before slot 0 needs it as its wrap-around source: keep a copy
             const int32_t oH = H1[M - 1], oE1 = E1r[M - 1], oE2 = E2r[M - 1];
+            const int bT0 = T0 >> 5;
+            const bool new_col = en == r;  // the cell (t = r, j = 0) enters on this anti-diagonal (it sits in block b_hi)
 #pragma unroll
             for (int m = M - 1; m >= 0; --m) {
                 // the block of 32 columns in [b_lo, b_hi] that maps to slot m, if any
@@ -178,21 +180,26 @@ static __device__ __noinline__ void kb_extd2_reg8(const KbDpConst P, int lane, i
                 int32_t upH = __shfl_up_sync(0xffffffffu, H1[m], 1), wH = __shfl_sync(0xffffffffu, sH, 31);
                 int32_t upE1 = __shfl_up_sync(0xffffffffu, E1r[m], 1), wE1 = __shfl_sync(0xffffffffu, sE1, 31);
                 int32_t upE2 = __shfl_up_sync(0xffffffffu, E2r[m], 1), wE2 = __shfl_sync(0xffffffffu, sE2, 31);
+                // Column t-1 of lane 0 is lane 31 of the previous block -- or, at the left edge of the rectangle / of the
+                // tile, the virtual column -1 / the previous tile's spilled last column (warp-uniform branches).
+                if (b == bT0) {
+                    if (T0 == 0) wH = -kb_gapcost2(P, r + 1), wE1 = wE2 = KB_NEG_INF;  // (t = -1, j = r)
+                    else if (lane == 0) {
+                        const int j = r - T0;
+                        wH = kb_ld_s32(ein + j), wE1 = kb_ld_s32(ein + KB_DP_MAXLEN + j), wE2 = kb_ld_s32(ein + 2 * KB_DP_MAXLEN + j);
+                    }
+                }
                 if (lane == 0) upH = wH, upE1 = wE1, upE2 = wE2;
                 const int t = (b << 5) + lane;
+                if (new_col && b == b_hi && t == r) {  // virtual row -1 for the column that starts now
+                    H1[m] = -kb_gapcost2(P, t + 1), F1r[m] = F2r[m] = KB_NEG_INF;
+                    HD[m] = t == 0 ? 0 : -kb_gapcost2(P, t);
+                }
                 if (t >= st && t <= en) {
                     const int j = r - t;
-                    int32_t h_up = upH, a1 = upE1, a2 = upE2, h_left = H1[m], b1 = F1r[m], b2 = F2r[m], h_diag = HD[m];
-                    if (t == 0 || j == 0 || t == T0) {  // rectangle / tile edges: a handful of lanes per anti-diagonal
-                        if (t == 0) h_up = -kb_gapcost2(P, j + 1), a1 = a2 = KB_NEG_INF;
-                        else if (t == T0) h_up = kb_ld_s32(ein + j), a1 = kb_ld_s32(ein + KB_DP_MAXLEN + j), a2 = kb_ld_s32(ein + 2 * KB_DP_MAXLEN + j);
-                        if (j == 0) h_left = -kb_gapcost2(P, t + 1), b1 = b2 = KB_NEG_INF;
-                        if (t == 0) h_diag = j == 0 ? 0 : -kb_gapcost2(P, j);
-                        else if (j == 0) h_diag = -kb_gapcost2(P, t);
-                        else if (t == T0) h_diag = kb_ld_s32(ein + j - 1);
-                    }
                     int d;
-                    const int32_t z = kb_cell(P, rb, h_up, a1, a2, h_left, b1, b2, h_diag, kb_ld_u8(ts + t), kb_ld_u8(qs + j), E1r[m], E2r[m], F1r[m], F2r[m], d);
+                    const int32_t z = kb_cell(P, rb, upH, upE1, upE2, H1[m], F1r[m], F2r[m], HD[m], kb_ld_u8(ts + t), kb_ld_u8(qs + j), E1r[m],
+                                              E2r[m], F1r[m], F2r[m], d);
                     HD[m] = upH;  // H(t-1, j): the diagonal neighbour of (t, j+1) on the next anti-diagonal
                     H1[m] = z;
                     kb_st_u8(pr + t, d);
