@@ -253,6 +253,8 @@ def run_ours(a):
     for _ in range(a.warmup):
         gi.map(batch, fetch=True)
     barrier()
+    dp_raw = np.zeros(32, dtype=np.int64)
+    L.kb_debug_dp_stats(None, 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -269,6 +271,13 @@ def run_ours(a):
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else {}
+    L.kb_debug_dp_stats(ptr(dp_raw), 0)
+    dp_stats = {}
+    for ki, kind in enumerate(("fill", "ext", "fill_zdrop")):
+        for pi, path in enumerate(("band_ok", "band_rejected", "reg", "reg_tiled", "scratch")):
+            c, n = int(dp_raw[2 * (5 * ki + pi)]), int(dp_raw[2 * (5 * ki + pi) + 1])
+            if c:
+                dp_stats[f"{kind}/{path}"] = {"calls": c // a.steps, "cells": n // a.steps}
     dev_ms = stage_acc.get("total", 0.0) / a.steps
     t = torch.tensor([wall, dev_ms], device=dev, dtype=torch.float64)
     if dist:
@@ -326,6 +335,7 @@ def run_ours(a):
         "device_ms_per_step": dev_ms_max,
         "stage_ms": {k: v / a.steps for k, v in stage_acc.items()},
         "counters": counters,
+        "dp_stats_per_step": dp_stats,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "assemblies_per_step": ne},
         "gpu_launches": int(counters.get("launches", 0)) * a.steps,

@@ -132,6 +132,11 @@ int kb_result_fetch_anchors(const kb_result_t *r, int32_t *out /* n x 7: asm,gen
 int kb_result_fetch_chains(const kb_result_t *r, int32_t *out /* n x 10: asm,gene,score,cnt,rev,rid,rs,re,qs,qe */, int64_t cap, int64_t *n);
 int kb_result_mid_occ(const kb_result_t *r, int32_t *out /* n_asm */);
 
+/* diagnostic: calls / cells of the base-level DP per (kind, path) since the last reset, process-wide on the current
+ * device; slot 2 * (5 * kind + path) = calls, + 1 = cells; kind 0 gap fill, 1 end extension, 2 gap fill with z-drop;
+ * path 0 band certified, 1 band rejected, 2 register single pass, 3 register tiled, 4 scratch-memory DP. */
+int kb_debug_dp_stats(int64_t *out32, int reset);
+
 /* one-call convenience for HOST buffers (the end-to-end path): batch_create +
  * map + fetch + destroy; copies are inside. */
 int kb_map_assemblies(const kb_index_t *idx,

@@ -29,6 +29,7 @@ struct KbAlignScratch {
     uint8_t *tfull;   // KB_TFULL_MAX target codes of [rs0, re0)
     uint32_t *cigar;  // KB_CIG_MAX, CIGAR of the hit being built
     uint32_t *ezcig;  // KB_CIG_MAX, CIGAR of the last DP
+    uint32_t *wmax;   // device only: 512-entry per-warp ring in shared memory (per-anti-diagonal maxima of kb_rows)
 };
 
 KB_HD size_t kb_align_scratch_bytes(int64_t max_sw_cells)
@@ -55,6 +56,7 @@ KB_HD KbAlignScratch kb_align_scratch_at(uint8_t *base, int64_t max_sw_cells)
     S.tbuf = p, p += KB_DP_MAXLEN;
     S.tfull = p, p += KB_TFULL_MAX;
     S.tb = p;
+    S.wmax = nullptr;
     (void)max_sw_cells;
     return S;
 }
@@ -285,6 +287,9 @@ KB_HD void kb_extd2(const KbDpConst P, int lane, int qlen, const uint8_t *qs, in
     kb_backtrack<NL>(lane, qlen, tlen, flag, ez, S);
 }
 
+#ifndef KB_DP_STAT
+#define KB_DP_STAT(kind, path, cells) ((void)0)
+#endif
 #ifdef __CUDACC__
 #define kb_backtrack_lane0(lane, qlen, tlen, flag, ez, S) kb_backtrack<32>(lane, qlen, tlen, flag, ez, S)
 #include "kb_align_reg.cuh"
@@ -293,12 +298,29 @@ static __device__ __noinline__ void kb_dp_device(const KbDpConst P, int lane, in
                                                  int w, int zdrop, int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
 {
     const int width = qlen < tlen ? qlen : tlen;
+    const int kind = (flag & KB_EZ_GLOBAL_NO_ZDROP) ? 0 : ((flag & KB_EZ_EXTZ_ONLY) ? 1 : 2);
+    (void)kind;
     // register paths need a band that never binds: every anti-diagonal is then a full slice of the rectangle
     const bool fits = qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN &&
                       w >= qlen + tlen;
-    if (fits && (width <= 32 * 7 || (flag & KB_EZ_GLOBAL_NO_ZDROP)))
-        kb_extd2_reg8(P, lane, qlen, qs, tlen, ts, zdrop, flag, width > 32 * 7, ez, S, cell_counter);
-    else kb_extd2<32>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+    if (fits && width > 32 && (flag & KB_EZ_GLOBAL_NO_ZDROP) && !(flag & KB_EZ_RIGHT)) {
+        const int ok = kb_global_band(P, lane, qlen, qs, tlen, ts, flag, ez, S, cell_counter);
+        if (lane == 0) KB_DP_STAT(kind, ok ? 0 : 1, (int64_t)32 * (qlen + tlen + 1));
+        if (ok) return;
+    }
+    // row-stripe wavefront for every rectangle within its limits (keys of the z-drop tracker hold 12 bits of t)
+    const bool track = !(flag & KB_EZ_GLOBAL_NO_ZDROP);
+    const int64_t tiles = (tlen + 255) / 256;
+    const int dlen = tlen > qlen ? tlen - qlen : qlen - tlen;
+    if (qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && tiles * (qlen + 31) * 256 <= P.max_sw_cells && (track || dlen < w) && w >= 2 &&
+        qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN && (!track || (qlen <= 4096 && tlen <= 4096))) {
+        if (lane == 0) KB_DP_STAT(kind, tiles > 1 ? 3 : 2, (int64_t)qlen * tlen);
+        if (track) kb_rows<8, true>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+        else kb_rows<8, false>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+    } else {
+        if (lane == 0) KB_DP_STAT(kind, 4, (int64_t)qlen * tlen);
+        kb_extd2<32>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+    }
 }
 #endif
 

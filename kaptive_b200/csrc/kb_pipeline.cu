@@ -5,6 +5,15 @@
 // for a GEMM); every stage that carries the path's arithmetic is the hand-written logic in
 // kb_scan.cuh / kb_chain.cuh / kb_align.cuh / kb_final.cuh.
 #include <cub/cub.cuh>
+// DP statistics (debug / profiling aid): calls and cells per (kind, path); kind 0 = gap fill, 1 = end extension,
+// 2 = gap fill redone with z-drop; path 0 = band certified, 1 = band rejected, 2 = register single pass,
+// 3 = register tiled, 4 = scratch-memory DP.  Slot = 2 * (5 * kind + path) (+1 for cells).
+__device__ unsigned long long g_kb_dp_stats[32];
+#define KB_DP_STAT(kind, path, cells)                                                       \
+    do {                                                                                    \
+        atomicAdd(&g_kb_dp_stats[2 * (5 * (kind) + (path))], 1ull);                         \
+        atomicAdd(&g_kb_dp_stats[2 * (5 * (kind) + (path)) + 1], (unsigned long long)(cells)); \
+    } while (0)
 #include "kb_final.cuh"
 #include "kb_kernels.h"
 
@@ -176,7 +185,11 @@ __global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexVie
 {
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
+    __shared__ uint32_t wmax_ring[4][512];
+    KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
+    S.wmax = wmax_ring[threadIdx.x >> 5];
+    for (int x = lane; x < 512; x += 32) S.wmax[x] = 0;
+    __syncwarp();
     int64_t cells = 0;
     for (;;) {
         unsigned long long ci = 0;
@@ -305,6 +318,16 @@ void kb_launch_group_flag(const uint64_t *skey, int64_t n, uint8_t *flag, cudaSt
         if (grid > 148 * 32) grid = 148 * 32;
         kb_group_flag_kernel<<<(unsigned)grid, 256, 0, st>>>(skey, n, flag);
     }
+}
+
+extern "C" int kb_debug_dp_stats(int64_t *out32, int reset)
+{
+    if (out32 && cudaMemcpyFromSymbol(out32, g_kb_dp_stats, sizeof(g_kb_dp_stats)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_kb_dp_stats, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------ stage dumps for parity tests

@@ -199,3 +199,25 @@ def test_full_size_assemblies_properties_and_oracle(env):
         ops, ln = cg & 0xF, cg >> 4
         assert int(ln[(ops == 0) | (ops == 1)].sum()) == int(h["q_end"][i] - h["q_start"][i])
         assert int(ln[(ops == 0) | (ops == 2)].sum()) == int(h["t_end"][i] - h["t_start"][i])
+
+
+def test_divergence_ladder_equals_oracle(env):
+    """Loci embedded at 0-14 % substitutions and 0-4 % indels: exercises the certified band pass of the gap fills on
+    both sides of its certificate (accepted, and rejected -> full DP) plus z-drop splits; every hit equals the oracle's."""
+    from kaptive_b200 import synth
+
+    db = synth.make_db(n_loci=12, genes_per_locus=10, n_core=3, seed=11)
+    gi = env["mapper"].GeneIndex(db.genes)
+    asms = []
+    for i in range(28):
+        s = 0.005 * i
+        asms.append(synth.make_assembly(db, i % 12, seed=7000 + i, genome_len=200_000, mean_contigs=4, sub=(s, s + 0.005),
+                                        indel=(0.0015 * i, 0.0015 * i + 0.001)))
+    res = gi.map_contigs([[s for _, s in a.contigs] for a in asms])
+    odb = ol.OracleDB(*db.flat())
+    total = 0
+    for ai, a in enumerate(asms):
+        ro = odb.map(*a.flat())
+        check_against(res, ai, ro["hits"], ro["cigar"])
+        total += len(ro["hits"])
+    assert total > 200
