@@ -315,8 +315,8 @@ static __device__ __noinline__ void kb_dp_device(const KbDpConst P, int lane, in
     if (qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && tiles * (qlen + 31) * 256 <= P.max_sw_cells && (track || dlen < w) && w >= 2 &&
         qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN && (!track || (qlen <= 4096 && tlen <= 4096))) {
         if (lane == 0) KB_DP_STAT(kind, tiles > 1 ? 3 : 2, (int64_t)qlen * tlen);
-        if (track) kb_rows<8, true>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
-        else kb_rows<8, false>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+        if (track) kb_rows<true>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+        else kb_rows<false>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
     } else {
         if (lane == 0) KB_DP_STAT(kind, 4, (int64_t)qlen * tlen);
         kb_extd2<32>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
