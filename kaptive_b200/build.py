@@ -28,7 +28,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return OUT
     OUT.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(OUT)] + [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
+    import os
+    import shlex
+
+    extra = shlex.split(os.environ.get("KB_NVCC_EXTRA", ""))  # experiments, e.g. -DKB_ALIGN_MINB=4
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(OUT)] + [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -287,6 +287,26 @@ KB_HD void kb_extd2(const KbDpConst P, int lane, int qlen, const uint8_t *qs, in
     kb_backtrack<NL>(lane, qlen, tlen, flag, ez, S);
 }
 
+// limits of the register-resident DP kernels (kb_rows); `track` = the per-anti-diagonal maximum is needed
+KB_HD bool kb_rows_eligible(int64_t max_sw_cells, int qlen, int tlen, int w, bool track)
+{
+    if (qlen <= 0 || tlen <= 0 || qlen > KB_DP_MAXLEN || tlen > KB_DP_MAXLEN) return false;
+    const int64_t tiles = (tlen + 255) / 256;
+    const int dlen = tlen > qlen ? tlen - qlen : qlen - tlen;
+    if ((int64_t)qlen * tlen > max_sw_cells || tiles * (qlen + 31) * 256 > max_sw_cells) return false;
+    if (w < 2 || (!track && dlen >= w)) return false;
+    if (track && (qlen > 4096 || tlen > 4096)) return false;
+    return true;
+}
+// the certified band pass is worth trying (kb_global_band re-checks its own margin)
+KB_HD bool kb_band_eligible(int64_t max_sw_cells, int qlen, int tlen, int w, int flag)
+{
+    const int width = qlen < tlen ? qlen : tlen;
+    const int dlen = tlen > qlen ? tlen - qlen : qlen - tlen;
+    return width > 32 && w >= qlen + tlen && (flag & KB_EZ_GLOBAL_NO_ZDROP) && !(flag & KB_EZ_RIGHT) && (63 - dlen) / 2 >= 8 &&
+           (int64_t)32 * (qlen + tlen + 8) <= max_sw_cells && (int64_t)qlen * tlen <= max_sw_cells;
+}
+
 #ifndef KB_DP_STAT
 #define KB_DP_STAT(kind, path, cells) ((void)0)
 #endif
@@ -297,26 +317,20 @@ KB_HD void kb_extd2(const KbDpConst P, int lane, int qlen, const uint8_t *qs, in
 static __device__ __noinline__ void kb_dp_device(const KbDpConst P, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts,
                                                  int w, int zdrop, int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
 {
-    const int width = qlen < tlen ? qlen : tlen;
     const int kind = (flag & KB_EZ_GLOBAL_NO_ZDROP) ? 0 : ((flag & KB_EZ_EXTZ_ONLY) ? 1 : 2);
     (void)kind;
-    // register paths need a band that never binds: every anti-diagonal is then a full slice of the rectangle
-    const bool fits = qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN &&
-                      w >= qlen + tlen;
-    if (fits && width > 32 && (flag & KB_EZ_GLOBAL_NO_ZDROP) && !(flag & KB_EZ_RIGHT)) {
-        const int ok = kb_global_band(P, lane, qlen, qs, tlen, ts, flag, ez, S, cell_counter);
+    const KbPtrSeq sq{qs}, st{ts};
+    if (kb_band_eligible(P.max_sw_cells, qlen, tlen, w, flag)) {
+        const int ok = kb_global_band(P, lane, qlen, sq, tlen, st, flag, ez, S, cell_counter);
         if (lane == 0) KB_DP_STAT(kind, ok ? 0 : 1, (int64_t)32 * (qlen + tlen + 1));
         if (ok) return;
     }
     // row-stripe wavefront for every rectangle within its limits (keys of the z-drop tracker hold 12 bits of t)
     const bool track = !(flag & KB_EZ_GLOBAL_NO_ZDROP);
-    const int64_t tiles = (tlen + 255) / 256;
-    const int dlen = tlen > qlen ? tlen - qlen : qlen - tlen;
-    if (qlen > 0 && tlen > 0 && (int64_t)qlen * tlen <= P.max_sw_cells && tiles * (qlen + 31) * 256 <= P.max_sw_cells && (track || dlen < w) && w >= 2 &&
-        qlen <= KB_DP_MAXLEN && tlen <= KB_DP_MAXLEN && (!track || (qlen <= 4096 && tlen <= 4096))) {
-        if (lane == 0) KB_DP_STAT(kind, tiles > 1 ? 3 : 2, (int64_t)qlen * tlen);
-        if (track) kb_rows<true>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
-        else kb_rows<false>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
+    if (kb_rows_eligible(P.max_sw_cells, qlen, tlen, w, track)) {
+        if (lane == 0) KB_DP_STAT(kind, tlen > 256 ? 3 : 2, (int64_t)qlen * tlen);
+        if (track) kb_rows<true>(P, lane, qlen, sq, tlen, st, w, zdrop, flag, ez, S, cell_counter);
+        else kb_rows<false>(P, lane, qlen, sq, tlen, st, w, zdrop, flag, ez, S, cell_counter);
     } else {
         if (lane == 0) KB_DP_STAT(kind, 4, (int64_t)qlen * tlen);
         kb_extd2<32>(P, lane, qlen, qs, tlen, ts, w, zdrop, flag, ez, S, cell_counter);
@@ -477,7 +491,8 @@ KB_HD void kb_filter_bad_seeds_alt(int as1, int cnt1, const uint64_t *ax, uint64
 }
 
 // minimap2 align.c mm_test_zdrop without the inversion test
-KB_HD int kb_test_zdrop(const kb_params_t &P, const uint8_t *qseq, const uint8_t *tseq, int n_cigar, const uint32_t *cigar)
+template <class SQ, class ST>
+KB_HD int kb_test_zdrop(const kb_params_t &P, SQ qseq, ST tseq, int n_cigar, const uint32_t *cigar)
 {
     int32_t score = 0, mx = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
     for (int k = 0; k < n_cigar; ++k) {
@@ -534,7 +549,8 @@ KB_HD void kb_append_cigar(KbReg &r, uint32_t *cigar, int n_cigar, const uint32_
 }
 
 // minimap2 align.c mm_fix_cigar + mm_update_extra (lane 0 only)
-KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, const uint8_t *qseq, const uint8_t *tseq)
+template <class SQ, class ST>
+KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, SQ qseq, ST tseq)
 {
     int32_t toff = 0, qoff = 0, to_shrink = 0, qshift = 0, tshift = 0;
     int n = r.n_cigar, k;
@@ -600,7 +616,7 @@ KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, cons
         }
         r.n_cigar = n;
     }
-    qseq += qshift, tseq += tshift;
+    qseq = qseq + qshift, tseq = tseq + tshift;
     toff = qoff = 0;
     double s = 0.0, mx = 0.0;
     r.blen = r.mlen = 0, r.n_ambi = 0;
@@ -620,9 +636,13 @@ KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, cons
             toff += len, qoff += len;
         } else if (op == 1 || op == 2) {
             int n_ambi = 0;
-            const uint8_t *sq = op == 1 ? qseq + qoff : tseq + toff;
-            for (uint32_t l = 0; l < len; ++l)
-                if (sq[l] > 3) ++n_ambi;
+            if (op == 1) {
+                for (uint32_t l = 0; l < len; ++l)
+                    if (qseq[qoff + l] > 3) ++n_ambi;
+            } else {
+                for (uint32_t l = 0; l < len; ++l)
+                    if (tseq[toff + l] > 3) ++n_ambi;
+            }
             r.blen += len - n_ambi, r.n_ambi += n_ambi;
             double pen = kb_dmul((double)P.e, (double)kb_log2_fast((float)(1.0 + len)));
             pen = kb_dadd((double)P.q, pen);
@@ -657,44 +677,31 @@ KB_HD void kb_split_reg(KbReg &r, KbReg &r2, int n, int qlen, const uint64_t *ax
     r.rev = t.rev, r.rid = t.rid, r.rs = t.rs, r.re = t.re, r.qs = t.qs, r.qe = t.qe;
 }
 
-// minimap2 align.c mm_align1 (long-read path).  ax/ay: the query's compacted anchors (n_a of them), minimap2 format.
-// Returns an error code (0 = ok); r2.cnt > 0 when the region was split by a z-drop.
-template <int NL>
-KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int asm_id, int gene, KbReg &r, KbReg &r2,
-                    int n_a, const uint64_t *ax, uint64_t *ay, const KbAlignScratch &S, int64_t *cell_counter)
+// first half of minimap2 align.c mm_align1: trimmed anchor range, first / last anchor and the query / target windows
+// the two end extensions may use.  Pure function of the chain and its (already seed-filtered) anchors.
+struct KbWin {
+    int32_t as1, cnt1, rs, qs, re, qe, rs0, qs0, re0, qe0;
+    int32_t rev, rid, ctg, tlen_full, qlen;
+    int64_t soff;
+};
+KB_HD void kb_align_window(const KbIndexView &ix, const KbBatchView &bt, int asm_id, int gene, int r_as, int r_cnt, int as1, int cnt1,
+                           int n_a, const uint64_t *ax, const uint64_t *ay, KbWin &W)
 {
     const kb_params_t &P = ix.p;
     const int qlen = ix.gene_len[gene];
-    const int32_t rid = (int32_t)(ax[r.as] << 1 >> 33), rev = (int32_t)(ax[r.as] >> 63);
+    const int32_t rid = (int32_t)(ax[r_as] << 1 >> 33), rev = (int32_t)(ax[r_as] >> 63);
     const int ctg = bt.asm_ctg_start[asm_id] + rid;
     const int32_t tlen_full = bt.ctg_len[ctg];
-    const int64_t soff = bt.ctg_soff[ctg];
-    const uint8_t *qseq0 = (rev ? ix.gseq_rev : ix.gseq_fwd) + ix.gene_seq_off[gene];
     const int hk = P.k >> 1;
-    int32_t as1, cnt1, i, l, bw, bw_long, dropped = 0, rs0, re0, qs0, qe0, rs, re, qs, qe, rs1, qs1, re1, qe1;
-    KbEz ez;
-
-    r2.cnt = 0;
-    if (r.cnt == 0) return 0;
-    bw = P.ext_bw;
-    bw_long = (int)(20000 * 1.5 + 1.);
-    if (bw_long < bw) bw_long = bw;
-
-    kb_fix_bad_ends(r.as, r.cnt, r.mlen, ax, ay, P.bw, P.min_chain_score * 2, &as1, &cnt1);
-    if (lane == 0) {  // the seed filters set flags in ay[]: one writer, then everyone reads
-        kb_filter_bad_seeds(as1, cnt1, ax, ay, 10, 40, P.max_gap >> 1, 10, S.off);
-        kb_filter_bad_seeds_alt(as1, cnt1, ax, ay, 30, P.max_gap >> 1, S.off);
-    }
-    kb_sync<NL>();
-
+    int32_t i, l, rs0, re0, qs0, qe0, rs, re, qs, qe, rs1, qs1, re1, qe1;
     rs = (int32_t)ax[as1] - hk, qs = (int32_t)ay[as1] - hk;
     re = (int32_t)ax[as1 + cnt1 - 1] - hk, qe = (int32_t)ay[as1 + cnt1 - 1] - hk;
 
-    rs0 = (int32_t)ax[r.as] + 1 - (int32_t)(ay[r.as] >> 32 & 0xff);
-    qs0 = (int32_t)ay[r.as] + 1 - (int32_t)(ay[r.as] >> 32 & 0xff);
+    rs0 = (int32_t)ax[r_as] + 1 - (int32_t)(ay[r_as] >> 32 & 0xff);
+    qs0 = (int32_t)ay[r_as] + 1 - (int32_t)(ay[r_as] >> 32 & 0xff);
     if (rs0 < 0) rs0 = 0;
     rs1 = qs1 = 0;
-    for (i = r.as - 1, l = 0; i >= 0 && ax[i] >> 32 == ax[r.as] >> 32; --i) {
+    for (i = r_as - 1, l = 0; i >= 0 && ax[i] >> 32 == ax[r_as] >> 32; --i) {
         int32_t x = (int32_t)ax[i] + 1 - (int32_t)(ay[i] >> 32 & 0xff);
         int32_t y = (int32_t)ay[i] + 1 - (int32_t)(ay[i] >> 32 & 0xff);
         if (x < rs0 && y < qs0) {
@@ -717,10 +724,10 @@ KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int 
         rs0 = rs0 < rs1 ? rs0 : rs1;
         rs0 = rs0 < rs ? rs0 : rs;
     } else rs0 = rs, qs0 = qs;
-    re0 = (int32_t)ax[r.as + r.cnt - 1] + 1;
-    qe0 = (int32_t)ay[r.as + r.cnt - 1] + 1;
+    re0 = (int32_t)ax[r_as + r_cnt - 1] + 1;
+    qe0 = (int32_t)ay[r_as + r_cnt - 1] + 1;
     re1 = tlen_full, qe1 = qlen;
-    for (i = r.as + r.cnt, l = 0; i < n_a && ax[i] >> 32 == ax[r.as] >> 32; ++i) {
+    for (i = r_as + r_cnt, l = 0; i < n_a && ax[i] >> 32 == ax[r_as] >> 32; ++i) {
         int32_t x = (int32_t)ax[i] + 1, y = (int32_t)ay[i] + 1;
         if (x > re0 && y > qe0) {
             if (++l > P.min_cnt) {
@@ -740,6 +747,41 @@ KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int 
         re1 = re1 < re + l ? re1 : re + l;
         re0 = re0 > re1 ? re0 : re1;
     } else re0 = re, qe0 = qe;
+    W.as1 = as1, W.cnt1 = cnt1, W.rs = rs, W.qs = qs, W.re = re, W.qe = qe, W.rs0 = rs0, W.qs0 = qs0, W.re0 = re0, W.qe0 = qe0;
+    W.rev = rev, W.rid = rid, W.ctg = ctg, W.tlen_full = tlen_full, W.qlen = qlen, W.soff = bt.ctg_soff[ctg];
+}
+
+// minimap2 align.c mm_align1 (long-read path).  ax/ay: the query's compacted anchors (n_a of them), minimap2 format.
+// Returns an error code (0 = ok); r2.cnt > 0 when the region was split by a z-drop.
+template <int NL>
+KB_HD int kb_align1(const KbIndexView &ix, const KbBatchView &bt, int lane, int asm_id, int gene, KbReg &r, KbReg &r2,
+                    int n_a, const uint64_t *ax, uint64_t *ay, const KbAlignScratch &S, int64_t *cell_counter)
+{
+    const kb_params_t &P = ix.p;
+    const int hk = P.k >> 1;
+    int32_t as1, cnt1, i, l, bw, bw_long, dropped = 0, rs0, re0, qs0, qe0, rs, re, qs, qe, rs1, qs1, re1, qe1;
+    KbEz ez;
+
+    r2.cnt = 0;
+    if (r.cnt == 0) return 0;
+    bw = P.ext_bw;
+    bw_long = (int)(20000 * 1.5 + 1.);
+    if (bw_long < bw) bw_long = bw;
+
+    kb_fix_bad_ends(r.as, r.cnt, r.mlen, ax, ay, P.bw, P.min_chain_score * 2, &as1, &cnt1);
+    if (lane == 0) {  // the seed filters set flags in ay[]: one writer, then everyone reads
+        kb_filter_bad_seeds(as1, cnt1, ax, ay, 10, 40, P.max_gap >> 1, 10, S.off);
+        kb_filter_bad_seeds_alt(as1, cnt1, ax, ay, 30, P.max_gap >> 1, S.off);
+    }
+    kb_sync<NL>();
+    KbWin W;
+    kb_align_window(ix, bt, asm_id, gene, r.as, r.cnt, as1, cnt1, n_a, ax, ay, W);
+    const int qlen = W.qlen, rev = W.rev;
+    const int32_t tlen_full = W.tlen_full;
+    (void)tlen_full, (void)l;
+    const int64_t soff = W.soff;
+    const uint8_t *qseq0 = (rev ? ix.gseq_rev : ix.gseq_fwd) + ix.gene_seq_off[gene];
+    rs = W.rs, qs = W.qs, re = W.re, qe = W.qe, rs0 = W.rs0, qs0 = W.qs0, re0 = W.re0, qe0 = W.qe0;
 
     if (re0 - rs0 > KB_TFULL_MAX || re0 <= rs0) return 2;
     // target window [rs0, re0) -> codes, cooperatively

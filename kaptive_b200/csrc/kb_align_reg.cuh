@@ -58,6 +58,28 @@ __device__ __forceinline__ int32_t kb_prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
+// sequence accessors of the DP kernels: element x of a query / target segment
+struct KbPtrSeq {  // plain nt4 bytes, forwards (the monolith's staged buffers)
+    const uint8_t *p;
+    __device__ __forceinline__ int operator()(int x) const { return kb_ld_u8(p + x); }
+};
+struct KbDirBytes {  // nt4 bytes, forwards (dir = 1) or backwards (dir = -1) from p
+    const uint8_t *p;
+    int dir;
+    __device__ __forceinline__ int operator()(int x) const { return kb_ld_u8(p + dir * x); }
+};
+struct KbDirPack {  // 2-bit + mask packed contig bases, forwards or backwards from pos
+    const uint32_t *seq2, *nmask;
+    int64_t pos;
+    int dir;
+    __device__ __forceinline__ int operator()(int x) const
+    {
+        const int64_t b = pos + (int64_t)dir * x;
+        if ((kb_ld_u32(nmask + (b >> 5)) >> (b & 31)) & 1u) return 4;
+        return (int)((kb_ld_u32(seq2 + (b >> 4)) >> (2 * (b & 15))) & 3u);
+    }
+};
+
 // constants of the x8 domain for one DP call
 struct KbC8 {
     int32_t oe1, oe2, of1, of2;  // open + first extension, with the tag of the state: -8 (q + e) + tag
@@ -101,17 +123,23 @@ __device__ __forceinline__ int kb_tb_state(uint32_t byte, int rb) { return rb ? 
 __device__ __forceinline__ int32_t kb_cell8(const KbC8 &c, int32_t hu, int32_t &e1, int32_t &e2, int32_t hl, int32_t &f1, int32_t &f2,
                                             int32_t hd, uint32_t srow, uint32_t sel, uint32_t &d)
 {
-    e1 = max(hu + c.oe1, e1 - c.x1);
-    e2 = max(hu + c.oe2, e2 - c.x2);
+    // the chain that links a row's cells runs hu -> (e1, e2) -> zk -> H8: everything else is computed off it
     f1 = max(hl + c.of1, f1 - c.x1);
     f2 = max(hl + c.of2, f2 - c.x2);
     const int32_t s = kb_prmt(srow, c.sN, sel);
-    int32_t zk = max(hd + s, e1);
-    zk = max(max(zk, f1), e2);
-    zk = max(zk, f2);
+    const int32_t pre = max(max(hd + s, f1), f2);
+    const int32_t x1 = e1 - c.x1, x2 = e2 - c.x2;
+    e1 = max(hu + c.oe1, x1);
+    e2 = max(hu + c.oe2, x2);
+    const int32_t zk = max(max(pre, e1), e2);
     const int32_t z = zk & ~7;
     const int32_t t1 = z + c.th1, t2 = z + c.th2;
-    d = (uint32_t)(zk & 7) + (e1 > t1 ? 0x08u : 0u) + (f1 > t1 ? 0x10u : 0u) + (e2 > t2 ? 0x20u : 0u) + (f2 > t2 ? 0x40u : 0u);
+    d = (uint32_t)(zk & 7);
+    asm("{\n\t.reg .pred p1, p2, p3, p4;\n\t"
+        "setp.gt.s32 p1, %1, %5;\n\tsetp.gt.s32 p2, %2, %5;\n\tsetp.gt.s32 p3, %3, %6;\n\tsetp.gt.s32 p4, %4, %6;\n\t"
+        "@p1 add.u32 %0, %0, 8;\n\t@p2 add.u32 %0, %0, 16;\n\t@p3 add.u32 %0, %0, 32;\n\t@p4 add.u32 %0, %0, 64;\n\t}"
+        : "+r"(d)
+        : "r"(e1), "r"(f1), "r"(e2), "r"(f2), "r"(t1), "r"(t2));
     return z;
 }
 
@@ -209,9 +237,9 @@ __device__ __forceinline__ void kb_band_step(const KbDpConst &P, const KbC8 &c, 
     acc = (acc >> 8) | (d << 24);
 }
 
-static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, int qlen, const uint8_t *__restrict__ qs, int tlen,
-                                                  const uint8_t *__restrict__ ts, int flag, KbEz &ez, const KbAlignScratch S,
-                                                  int64_t *cell_counter)
+template <class SQ, class ST>
+static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, int qlen, const SQ qs, int tlen, const ST ts, int flag, KbEz &ez,
+                                                  const KbAlignScratch S, int64_t *cell_counter)
 {
     const int d1 = tlen - qlen, lo_d = d1 < 0 ? d1 : 0, hi_d = d1 > 0 ? d1 : 0;
     const int margin = (63 - (hi_d - lo_d)) >> 1;
@@ -235,25 +263,25 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
             if (stepB) ++tp;
             else ++jp;
         }
-        srow = kb_score_row(P, c, kb_ld_u8(ts + (tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1)));
-        sel = kb_score_sel(kb_ld_u8(qs + (jp < 1 ? 0 : (jp > qlen ? qlen : jp) - 1)));
+        srow = kb_score_row(P, c, ts((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1)));
+        sel = kb_score_sel(qs((jp < 1 ? 0 : (jp > qlen ? qlen : jp) - 1)));
         kb_band_step<true>(P, c, lane, stepB, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
     }
     // interior: every in-range cell has real neighbours; cells past the far edges compute garbage nobody reads
     for (; rp + 1 <= r_end; rp += 2) {
         ++jp;
-        sel = kb_score_sel(kb_ld_u8(qs + (jp > qlen ? qlen : jp) - 1));
+        sel = kb_score_sel(qs((jp > qlen ? qlen : jp) - 1));
         kb_band_step<false>(P, c, lane, false, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
         ++tp;
-        srow = kb_score_row(P, c, kb_ld_u8(ts + (tp > tlen ? tlen : tp) - 1));
+        srow = kb_score_row(P, c, ts((tp > tlen ? tlen : tp) - 1));
         kb_band_step<false>(P, c, lane, true, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if (((rp + 1) & 3) == 3) kb_st_u32(tbw + ((rp + 1) >> 2) * 32 + lane, acc);
     }
     if (rp == r_end) {
         ++jp;
-        sel = kb_score_sel(kb_ld_u8(qs + (jp > qlen ? qlen : jp) - 1));
+        sel = kb_score_sel(qs((jp > qlen ? qlen : jp) - 1));
         kb_band_step<false>(P, c, lane, false, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
     }
@@ -299,39 +327,54 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
 // conflict free: lanes sit K - 1 anti-diagonals apart), the ring is drained into rmax[r] every 256 steps, and the
 // sequential z-drop rule runs over rmax[] after the last tile.  Cells beyond a z-drop are computed in vain but
 // never influence the result (a traceback only moves towards smaller r).
+template <bool MASK, bool TRACK, int M>
+__device__ __forceinline__ void kb_rows_cell(const KbC8 &c, int w, int d0, int nvm, unsigned ring, int rbase, int32_t ckey, uint32_t sel,
+                                             int32_t &hu, int32_t &e1, int32_t &e2, int32_t &hd, int32_t (&Hc)[8], int32_t (&F1)[8],
+                                             int32_t (&F2)[8], const uint32_t (&srow)[8], uint32_t (&tbw)[2])
+{
+    uint32_t d;
+    const int32_t hl = Hc[M];
+    int32_t z = kb_cell8(c, hu, e1, e2, hl, F1[M], F2[M], hd, srow[M], sel, d);
+    bool ok = true;
+    if (MASK) {
+        ok = (unsigned)(d0 + M + w) <= (unsigned)(2 * w);
+        if (!ok) z = e1 = e2 = F1[M] = F2[M] = KB_NEG8, d = 0;
+    }
+    hd = hl, Hc[M] = z, hu = z;
+    tbw[M >> 2] += d << (8 * (M & 3));
+    if (TRACK) {
+        if (M < nvm && ok) {
+            const uint32_t key = (uint32_t)(z * 512 + (ckey - M));
+            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring + (((unsigned)(rbase + M) & 511u) << 2)), "r"(key) : "memory");
+        }
+    }
+}
+// One row of a lane's stripe.  A stripe of kact < 8 columns lives in the LAST kact slots, so the row is one jump
+// into the unrolled sequence (slot 8 - kact) and no per-cell test.
 template <bool MASK, bool TRACK>
-__device__ __forceinline__ void kb_rows_body(const KbC8 &c, int kact, int w, int d0, int nval, unsigned ring, int rbase, int32_t ckey,
+__device__ __forceinline__ void kb_rows_body(const KbC8 &c, int kact, int w, int d0, int nvm, unsigned ring, int rbase, int32_t ckey,
                                              uint32_t sel, int32_t &hu, int32_t &e1, int32_t &e2, int32_t &hd, int32_t (&Hc)[8],
                                              int32_t (&F1)[8], int32_t (&F2)[8], const uint32_t (&srow)[8], uint32_t (&tbw)[2])
 {
     tbw[0] = tbw[1] = 0;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        if (m >= kact) break;  // warp-uniform
-        uint32_t d;
-        const int32_t hl = Hc[m];
-        int32_t z = kb_cell8(c, hu, e1, e2, hl, F1[m], F2[m], hd, srow[m], sel, d);
-        bool ok = true;
-        if (MASK) {
-            ok = (unsigned)(d0 + m + w) <= (unsigned)(2 * w);
-            if (!ok) z = e1 = e2 = F1[m] = F2[m] = KB_NEG8, d = 0;
-        }
-        hd = hl, Hc[m] = z, hu = z;
-        tbw[m >> 2] |= d << (8 * (m & 3));
-        if (TRACK) {
-            if (m < nval && ok) {
-                const uint32_t key = (uint32_t)(z * 512 + (ckey - m));
-                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring + (((unsigned)(rbase + m) & 511u) << 2)), "r"(key) : "memory");
-            }
-        }
+#define KB_RC(M) kb_rows_cell<MASK, TRACK, M>(c, w, d0, nvm, ring, rbase, ckey, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw)
+    switch (kact) {
+    case 8: KB_RC(0);
+    case 7: KB_RC(1);
+    case 6: KB_RC(2);
+    case 5: KB_RC(3);
+    case 4: KB_RC(4);
+    case 3: KB_RC(5);
+    case 2: KB_RC(6);
+    default: KB_RC(7);
     }
+#undef KB_RC
 }
 
 #define KB_ROWS_KEY_BIAS (int32_t)(0x80000000u + 4095u)
-template <bool TRACK>
-static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qlen, const uint8_t *__restrict__ qs, int tlen,
-                                            const uint8_t *__restrict__ ts, int w, int zdrop, int flag, KbEz &ez, const KbAlignScratch S,
-                                            int64_t *cell_counter)
+template <bool TRACK, class SQ, class ST>
+static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qlen, const SQ qs, int tlen, const ST ts, int w, int zdrop,
+                                            int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
 {
     const int rb = (flag & KB_EZ_RIGHT) ? 1 : 0;
     const KbC8 c = kb_c8(P, rb);
@@ -362,25 +405,33 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
     int32_t score = KB_NEG_INF;
     for (int tile = 0; tile < ntile; ++tile) {
         const bool spill = tile + 1 < ntile;  // then the tile is full width and its last column is lane 31's last
-        const int kact = spill ? 8 : klast;
-        const int T0 = tile << 8, t0 = T0 + lane * kact;
+        const int kact = spill ? 8 : klast, koff = 8 - kact;
+        const int T0 = tile << 8, t0 = T0 + lane * kact, t0s = t0 - koff;  // slot m holds column t0s + m (m >= koff)
         const int32_t *ein = edge + (size_t)((tile & 1) ^ 1) * 3 * KB_DP_MAXLEN;
         int32_t *eout = edge + (size_t)(tile & 1) * 3 * KB_DP_MAXLEN;
         int32_t Hc[8], F1[8], F2[8];
         uint32_t srow[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int t = t0 + m;
+            const int t = t0s + m;
             Hc[m] = -8 * kb_gapcost2(P, t + 1), F1[m] = kb_neg_f1(c), F2[m] = kb_neg_f2(c);  // virtual row j = -1
-            srow[m] = kb_score_row(P, c, (m < kact && t < tlen) ? kb_ld_u8(ts + t) : 4);
+            srow[m] = kb_score_row(P, c, (m >= koff && t < tlen) ? ts(t) : 4);
         }
         int nval = tlen - t0;
         nval = nval < 0 ? 0 : (nval > kact ? kact : nval);
+        const int nvm = nval > 0 ? koff + nval : 0;  // slots below nvm hold real columns
         // what the lane offers to lane + 1: (H, E1, E2) of its last column in the row it has just finished
         int32_t oh = -8 * kb_gapcost2(P, t0 + kact), oe1 = kb_neg_e1(c), oe2 = kb_neg_e2(c);
         int32_t dg = T0 == 0 ? 0 : -8 * kb_gapcost2(P, T0);  // lane 0: H(T0 - 1, -1); other lanes: set by the first shuffle
         uint8_t *tbt = tb + (size_t)tile * tile_bytes + lane * 8;
+        int cq_next = qs((lane == 0 ? 0 : qlen - 1));  // row 0 is lane 0's first; the others reload before use
         for (int s = 0; s < nstep; ++s) {
+            const int cq = cq_next;
+            {
+                int jn = s + 1 - lane;
+                jn = jn < 0 ? 0 : (jn >= qlen ? qlen - 1 : jn);
+                cq_next = qs(jn);
+            }
             int32_t uh = __shfl_up_sync(0xffffffffu, oh, 1), ue1 = __shfl_up_sync(0xffffffffu, oe1, 1), ue2 = __shfl_up_sync(0xffffffffu, oe2, 1);
             const int j = s - lane;
             const bool act = (unsigned)j < (unsigned)qlen;
@@ -388,19 +439,19 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
                 if (T0 == 0) uh = -8 * kb_gapcost2(P, j + 1), ue1 = kb_neg_e1(c), ue2 = kb_neg_e2(c);
                 else uh = kb_ld_s32(ein + j), ue1 = kb_ld_s32(ein + KB_DP_MAXLEN + j), ue2 = kb_ld_s32(ein + 2 * KB_DP_MAXLEN + j);
             }
-            const int d0 = t0 - j;
-            const bool edge_lane = banded && act && (d0 < -w || d0 + kact - 1 > w);
+            const int d0 = t0s - j;  // diagonal of slot 0
+            const bool edge_lane = banded && act && (d0 + koff < -w || d0 + 7 > w);
             const bool any_edge = banded && __any_sync(0xffffffffu, edge_lane);
             if (act) {
-                const uint32_t sel = kb_score_sel(kb_ld_u8(qs + j));
+                const uint32_t sel = kb_score_sel(cq);
                 int32_t hu = uh, e1 = ue1, e2 = ue2, hd = dg;
                 uint32_t tbw[2];
-                if (any_edge) kb_rows_body<true, TRACK>(c, kact, w, d0, nval, ring, t0 + j, KB_ROWS_KEY_BIAS - t0, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
-                else kb_rows_body<false, TRACK>(c, kact, w, d0, nval, ring, t0 + j, KB_ROWS_KEY_BIAS - t0, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
+                if (any_edge) kb_rows_body<true, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
+                else kb_rows_body<false, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
                 oh = hu, oe1 = e1, oe2 = e2;
                 uint32_t *dst = reinterpret_cast<uint32_t *>(tbt + (size_t)s * 256);  // a lane's slot is 8 bytes wide whatever kact is
-                kb_st_u32(dst, tbw[0]);
-                if (kact > 4) kb_st_u32(dst + 1, tbw[1]);
+                kb_st_u32(dst + 1, tbw[1]);
+                if (kact > 4) kb_st_u32(dst, tbw[0]);
                 if (spill && lane == 31) kb_st_s32(eout + j, oh), kb_st_s32(eout + KB_DP_MAXLEN + j, oe1), kb_st_s32(eout + 2 * KB_DP_MAXLEN + j, oe2);
             }
             dg = uh;
@@ -408,7 +459,7 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
         }
         if (TRACK) drain(T0 + nstep - 288), drain(T0 + nstep + 224);
         if (!spill) {  // H(tlen - 1, qlen - 1): the last row of column tlen - 1
-            const int cc = tlen - 1 - T0, ms = cc % kact;
+            const int cc = tlen - 1 - T0, ms = koff + cc % kact;
             int32_t hv = Hc[0];
 #pragma unroll
             for (int m = 1; m < 8; ++m)
@@ -450,7 +501,7 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
     z_.n_cigar = kb_backtrack_warp(lane, i, j, rb, flag, S.ezcig, [&](int ii, int jj) -> uint32_t {
         const int tile = ii >> 8, cc = ii & 255, kk = tile + 1 < ntile ? 8 : klast;
         const int l = cc / kk;
-        return (uint32_t)kb_ld_u8(tb + (size_t)tile * tile_bytes + (size_t)(jj + l) * 256 + l * 8 + (cc - l * kk));
+        return (uint32_t)kb_ld_u8(tb + (size_t)tile * tile_bytes + (size_t)(jj + l) * 256 + l * 8 + (8 - kk) + (cc - l * kk));
     });
     ez = z_;
 }

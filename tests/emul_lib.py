@@ -89,4 +89,5 @@ class EmulIndex:
         lib().kbe_result_fetch(r, _ptr(hits), _ptr(cigar), _ptr(anchors), _ptr(chains), _ptr(mzh), _ptr(mzc), _ptr(mzp))
         lib().kbe_result_free(r)
         return {"hits": hits, "cigar": cigar, "anchors": anchors, "chains": chains, "mid_occ": int(cnt[4]),
-                "n_minimizers": int(cnt[5]), "mz_hash": mzh, "mz_ctg": mzc, "mz_pos": mzp}
+                "n_minimizers": int(cnt[5]), "mz_hash": mzh, "mz_ctg": mzc, "mz_pos": mzp,
+                "stage": {"ok": int(cnt[7]) & 0x1FFFFF, "fallback": (int(cnt[7]) >> 21) & 0x1FFFFF, "mismatch": int(cnt[7]) >> 42}}

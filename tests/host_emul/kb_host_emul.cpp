@@ -10,6 +10,7 @@
 #include "../../kaptive_b200/csrc/kb_host.h"
 #include "../../kaptive_b200/csrc/kb_scan.cuh"
 #include "../../kaptive_b200/csrc/kb_final.cuh"
+#include "../../kaptive_b200/csrc/kb_stage.cuh"
 
 // same helpers the scan kernel defines (kb_scan.cu is a .cu file; restated here for the host build)
 static inline bool ht_lookup(const uint64_t *ht, uint32_t ht_mask, uint32_t hash, uint32_t *start, uint32_t *count)
@@ -43,6 +44,7 @@ struct EmuResult {
     std::vector<int32_t> mz_ctg;
     int32_t mid_occ = 0;
     int64_t n_minimizers = 0;
+    int64_t stage_ok = 0, stage_fallback = 0, stage_mismatch = 0;  // staged path (kb_stage.cuh) vs kb_align1, per chain
 };
 
 struct PackedFetch {
@@ -204,6 +206,38 @@ EmuResult *kbe_map_assembly(void *idx_, const uint8_t *ascii, const int64_t *ctg
         r.as = c.as, r.cnt = c.cnt, r.score = c.score, r.score0 = c.score0, r.mlen = c.mlen, r.blen = c.blen, r.parent = c.parent, r.id = reg_idx;
         r.hash = c.hash, r.rev = c.rev, r.rid = c.rid, r.rs = c.rs, r.re = c.re, r.qs = c.qs, r.qe = c.qe;
         int32_t subsc = c.subsc, n_sub = c.n_sub;
+        // staged path (plan -> one DP per job -> assemble), checked against kb_align1 below
+        KbReg rst = r;
+        std::vector<uint32_t> cig_st;
+        int staged = -1;
+        {
+            KbPlan pl;
+            std::vector<KbJob> jobs(KB_JOBS_PER_CHAIN_MAX);
+            std::vector<int32_t> K((size_t)gi.n_a + 8);
+            int nj = kb_stage_plan(ix, bt, gi.asm_id, gi.gene, r.as, r.cnt, r.mlen, gi.n_a, cx.data() + gi.a_base, cy.data() + gi.a_base,
+                                   K.data(), pl, jobs.data());
+            if (nj >= 0) {
+                std::vector<uint32_t> jobcig;
+                const uint8_t *gq = c.rev ? ix.gseq_rev : ix.gseq_fwd;
+                for (int k = 0; k < nj; ++k) {
+                    KbJob &J = jobs[(size_t)k];
+                    std::vector<uint8_t> q((size_t)J.qlen), t((size_t)J.tlen);
+                    const bool back = J.kind == KB_JOB_LEFT;
+                    for (int x = 0; x < J.qlen; ++x) q[(size_t)x] = back ? gq[J.qbase + J.qoff - 1 - x] : gq[J.qbase + J.qoff + x];
+                    for (int x = 0; x < J.tlen; ++x)
+                        t[(size_t)x] = (uint8_t)kb_fetch_base(bt.seq2, bt.nmask, back ? J.tpos - 1 - x : J.tpos + x);
+                    KbEz ez;
+                    int64_t dummy = 0;
+                    kb_extd2<1>(kb_dp_const(P), 0, J.qlen, q.data(), J.tlen, t.data(), J.w, J.zdrop, J.flag, ez, S, &dummy);
+                    J.score = ez.score, J.max = ez.max, J.max_t = ez.max_t, J.max_q = ez.max_q, J.zdropped = ez.zdropped, J.n_cigar = ez.n_cigar;
+                    J.cigar_off = (int64_t)jobcig.size(), J.state = 1;
+                    for (int x = 0; x < ez.n_cigar; ++x) jobcig.push_back(S.ezcig[x]);
+                }
+                cig_st.assign(jobcig.size() + 8, 0);
+                jobcig.push_back(0);
+                staged = kb_stage_assemble(ix, bt, gi.gene, pl, jobs.data(), jobcig.data(), rst, cig_st.data());
+            }
+        }
         for (int split = 0;; ++split) {
             KbReg r2;
             memset(&r2, 0, sizeof(r2));
@@ -217,6 +251,18 @@ EmuResult *kbe_map_assembly(void *idx_, const uint8_t *ascii, const int64_t *ctg
             h.parent = r.parent, h.subsc = subsc, h.n_sub = n_sub, h.n_cigar = e ? 0 : r.n_cigar, h.err = e;
             h.cigar_off = (int64_t)pool.size();
             for (int i = 0; i < h.n_cigar; ++i) pool.push_back(S.cigar[i]);
+            if (split == 0) {
+                if (staged != 0) ++R->stage_fallback;
+                else {
+                    bool same = e == 0 && r2.cnt == 0 && rst.cnt == r.cnt && rst.score == r.score && rst.rs == r.rs && rst.re == r.re &&
+                                rst.qs == r.qs && rst.qe == r.qe && rst.has_p == r.has_p && rst.dp_score == r.dp_score &&
+                                rst.dp_max == r.dp_max && rst.n_ambi == r.n_ambi && rst.mlen == r.mlen && rst.blen == r.blen &&
+                                rst.n_cigar == r.n_cigar;
+                    for (int i = 0; same && i < r.n_cigar; ++i) same = cig_st[(size_t)i] == S.cigar[i];
+                    if (same) ++R->stage_ok;
+                    else ++R->stage_mismatch;
+                }
+            }
             raw.push_back(h);
             if (e == 0 && r2.cnt > 0) r = r2;
             else break;
@@ -250,6 +296,7 @@ int64_t kbe_result_counts(EmuResult *r, int64_t *out)
 {
     out[0] = (int64_t)r->hits.size(), out[1] = (int64_t)r->cigar.size(), out[2] = (int64_t)r->anchors.size();
     out[3] = (int64_t)r->chains.size(), out[4] = r->mid_occ, out[5] = r->n_minimizers, out[6] = (int64_t)r->mz_hash.size();
+    out[7] = r->stage_mismatch << 42 | r->stage_fallback << 21 | r->stage_ok;
     return 0;
 }
 void kbe_result_fetch(EmuResult *r, EmuHit *hits, uint32_t *cigar, EmuAnchor *anchors, EmuChain *chains, uint32_t *mzh, int32_t *mzc, uint32_t *mzp)

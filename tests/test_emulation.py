@@ -36,6 +36,7 @@ def test_emulation_matches_golden(name):
     r = emul_index(db).map(*cases.flat_contigs(contigs), lane_bases=256, keep_stages=True)
     assert_same(r, GOLD[f"{name}/hits"], GOLD[f"{name}/cigar"], GOLD[f"{name}/chains"])
     assert [r["mid_occ"], r["n_minimizers"], len(r["anchors"])] == list(GOLD[f"{name}/meta"])
+    assert r["stage"]["mismatch"] == 0  # staged plan -> jobs -> assemble path == kb_align1 wherever it claims the chain
 
 
 @pytest.mark.parametrize("lane_bases", [1, 7, 24, 25, 64, 1000, -1, -9, -10, -11, -256, -100000])
@@ -84,6 +85,24 @@ def test_random_cases_against_oracle():
         ro = odb.map(*a.flat(), keep_stages=True)
         re = edb.map(*a.flat(), lane_bases=(256, 100, 33)[s % 3], keep_stages=True)
         assert_same(re, ro["hits"], ro["cigar"], ro["chains"])
+        assert re["stage"]["mismatch"] == 0 and re["stage"]["ok"] > 0
+
+
+def test_staged_alignment_equals_monolith_on_divergence_ladder():
+    """kb_stage.cuh (plan, per-job DP, assemble) against kb_align1 chain by chain, 0-14 % substitutions / 0-4 % indels."""
+    from kaptive_b200 import synth
+
+    db = synth.make_db(n_loci=12, genes_per_locus=10, n_core=3, seed=11)
+    edb = el.EmulIndex(*db.flat())
+    ok = fb = 0
+    for i in range(0, 28, 3):
+        s = 0.005 * i
+        a = synth.make_assembly(db, i % 12, seed=7000 + i, genome_len=200_000, mean_contigs=4, sub=(s, s + 0.005),
+                                indel=(0.0015 * i, 0.0015 * i + 0.001))
+        r = edb.map(*a.flat())
+        assert r["stage"]["mismatch"] == 0
+        ok, fb = ok + r["stage"]["ok"], fb + r["stage"]["fallback"]
+    assert ok > 100 and ok > 5 * fb
 
 
 def test_fast_sketch_on_low_complexity_sequence():
