@@ -33,7 +33,17 @@ void kb_launch_chain(const KbIndexView &, const KbBatchView &, const uint64_t *,
                      unsigned long long *, int64_t, cudaStream_t);
 void kb_launch_align(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
                      uint64_t *, uint8_t *, size_t, int, KbRawHit *, int64_t, uint32_t *, int64_t, unsigned long long *,
-                     unsigned long long *, cudaStream_t);
+                     unsigned long long *, const int32_t *, const unsigned long long *, cudaStream_t);
+size_t kb_band_scratch_bytes();
+size_t kb_sizeof_job();
+size_t kb_sizeof_plan();
+void kb_launch_stage_plan(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
+                          uint64_t *, int32_t *, void *, void *, int64_t, int32_t *, int32_t *, int32_t *, unsigned long long *, cudaStream_t);
+void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, int32_t *, int32_t *, uint8_t *, int, uint8_t *, size_t, int,
+                        uint32_t *, int64_t, unsigned long long *, cudaStream_t);
+void kb_launch_stage_assemble(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const void *,
+                              const void *, const uint32_t *, uint32_t *, int64_t, KbRawHit *, int64_t, uint32_t *, int64_t, int32_t *,
+                              unsigned long long *, cudaStream_t);
 void kb_launch_rawkey(const KbRawHit *, int64_t, uint64_t *, uint32_t *, cudaStream_t);
 void kb_launch_gather_raw(const KbRawHit *, const uint32_t *, int64_t, KbRawHit *, cudaStream_t);
 void kb_launch_finalize(const kb_params_t &, KbRawHit *, int64_t, const KbGroupInfo *, int32_t *, uint64_t *, int32_t *, cudaStream_t);
@@ -575,12 +585,42 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         }
         uint8_t *scratch = P.get<uint8_t>((size_t)n_warps * sbytes);
         unsigned long long *d_next = P.get<unsigned long long>(1);
+        // staged path (kb_stage.cuh): plan -> band / rows DP kernels -> assemble; what it hands back goes to kb_align_kernel
+        const char *sg = getenv("KAPTIVE_B200_STAGED");
+        const bool staged = !(sg && sg[0] == '0') && n_chains > 0;
+        const int64_t job_cap = n_chains * 12 + 4096, jobcig_cap = job_cap * 16;
+        const int band_warps = bt->n_sm * 16, rows_warps = n_warps;
+        void *plans = nullptr, *jobs = nullptr;
+        int32_t *band_list = nullptr, *rows_list = nullptr, *slow_list = nullptr, *kscratch = nullptr;
+        uint32_t *jobcig = nullptr, *tmpcig = nullptr;
+        uint8_t *band_scratch = nullptr;
+        if (staged) {
+            plans = P.get<uint8_t>((size_t)n_chains * kb_sizeof_plan());
+            jobs = P.get<uint8_t>((size_t)job_cap * kb_sizeof_job());
+            band_list = P.get<int32_t>((size_t)job_cap), rows_list = P.get<int32_t>((size_t)job_cap);
+            slow_list = P.get<int32_t>((size_t)n_chains + 1), kscratch = P.get<int32_t>((size_t)n_anchors + 8);
+            jobcig = P.get<uint32_t>((size_t)jobcig_cap), tmpcig = P.get<uint32_t>((size_t)jobcig_cap + (size_t)n_chains + 8);
+            band_scratch = P.get<uint8_t>((size_t)band_warps * kb_band_scratch_bytes());
+        }
         for (int attempt = 0;; ++attempt) {
             CU(cudaMalloc((void **)&pool, (size_t)pool_cap * 4 + 16));
             CU(cudaMemsetAsync(d_next, 0, 8, st));
             CU(cudaMemsetAsync(d_counters + 4, 0, 16, st));
-            CU(cudaMemsetAsync(d_counters + 8, 0, 8, st));
-            kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next, st);
+            CU(cudaMemsetAsync(d_counters + 8, 0, 8 * 8, st));
+            CU(cudaMemsetAsync(d_counters + 32, 0, 8 * 8, st));
+            if (staged) {
+                kb_launch_stage_plan(iv, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, job_cap, band_list, rows_list, slow_list,
+                                     d_counters, st);
+                kb_launch_stage_dp(iv, bv, jobs, band_list, rows_list, band_scratch, band_warps, scratch, sbytes, rows_warps, jobcig, jobcig_cap,
+                                   d_counters, st);
+                kb_launch_stage_assemble(iv, bv, chains, n_chains, ginfo, plans, jobs, jobcig, tmpcig, jobcig_cap + n_chains, raw, raw_cap, pool,
+                                         pool_cap, slow_list, d_counters, st);
+                kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next,
+                                slow_list, d_counters + 12, st);
+                launches += 4;
+            } else
+                kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next,
+                                nullptr, nullptr, st);
             ++launches;
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
@@ -594,7 +634,12 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             pool_cap = n_pool + 1024;
         }
         R->pool = pool, R->owned.push_back(pool), R->n_cigar = n_pool;
+        R->counters[7] = (int64_t)hc[12];  // chains the staged path handed back to kb_align_kernel
         P.release(scratch);
+        if (staged) {
+            P.release(plans), P.release(jobs), P.release(band_list), P.release(rows_list), P.release(slow_list), P.release(kscratch);
+            P.release(jobcig), P.release(tmpcig), P.release(band_scratch);
+        }
         CU(cudaEventRecord(ev[4], st));
         R->counters[4] = n_raw, R->counters[6] = (int64_t)hc[8];
 

@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 
 // counters: [0] minimizers, [1] anchors, [2] groups, [3] chains, [4] raw hits, [5] cigar words, [6] error bits, [7] debug dump count, [8] DP cells
-#define KB_N_COUNTERS 32  // [0..15] main pipeline, [16..31] auxiliary scans (census, dumps)
+#define KB_N_COUNTERS 48  // [0..15] main pipeline, [16..31] auxiliary scans (census, dumps), [32..] staged-alignment queue cursors
 
 void kb_launch_scan(const KbIndexView &ix, const KbBatchView &bt, uint64_t *akey, uint32_t *aval,
                     unsigned long long *counters, int64_t anchor_cap, uint32_t *mz_hash, int32_t *mz_ctg,

@@ -15,6 +15,7 @@ __device__ unsigned long long g_kb_dp_stats[32];
         atomicAdd(&g_kb_dp_stats[2 * (5 * (kind) + (path)) + 1], (unsigned long long)(cells)); \
     } while (0)
 #include "kb_final.cuh"
+#include "kb_stage.cuh"
 #include "kb_kernels.h"
 
 // ------------------------------------------------------------------ pack: ASCII -> 2 bit + N mask
@@ -181,8 +182,10 @@ void kb_launch_chain(const KbIndexView &ix, const KbBatchView &bt, const uint64_
 __global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
                                                        const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, uint8_t *scratch,
                                                        size_t scratch_bytes, KbRawHit *raw, int64_t raw_cap, uint32_t *pool,
-                                                       int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain)
+                                                       int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain,
+                                                       const int32_t *list, const unsigned long long *n_list)
 {
+    if (list) n_chains = (int64_t)*n_list;  // only the chains the staged path handed back
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     __shared__ uint32_t wmax_ring[4][512];
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexVie
         if (lane == 0) ci = atomicAdd(next_chain, 1ull);
         ci = __shfl_sync(0xffffffffu, ci, 0);
         if ((int64_t)ci >= n_chains) break;
+        if (list) ci = (unsigned long long)list[ci];
         const KbChainRec c = chains[ci];
         const KbGroupInfo gi = ginfo[c.group];
         KbReg r;
@@ -238,11 +242,223 @@ __global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexVie
 void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
                      const uint64_t *cx, uint64_t *cy, uint8_t *scratch, size_t scratch_bytes, int n_warps, KbRawHit *raw,
                      int64_t raw_cap, uint32_t *pool, int64_t pool_cap, unsigned long long *counters, unsigned long long *next_chain,
-                     cudaStream_t st)
+                     const int32_t *list, const unsigned long long *n_list, cudaStream_t st)
 {
     if (n_chains <= 0) return;
     kb_align_kernel<<<(unsigned)(n_warps / 4), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, scratch, scratch_bytes, raw, raw_cap,
-                                                             pool, pool_cap, counters, next_chain);
+                                                             pool, pool_cap, counters, next_chain, list, n_list);
+}
+
+// ------------------------------------------------------------------ staged alignment (kb_stage.cuh)
+// counters used by the staged path (d_counters + KB_SC_*)
+#define KB_SC_JOBS 9
+#define KB_SC_BAND 10
+#define KB_SC_ROWS 11
+#define KB_SC_SLOW 12
+#define KB_SC_JOBCIG 13
+#define KB_SC_TMPCIG 14
+#define KB_SC_QBAND 32
+#define KB_SC_QROWS 33
+
+__global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
+                                                      const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, int32_t *kscratch,
+                                                      KbPlan *plans, KbJob *jobs, int64_t job_cap, int32_t *band_list, int32_t *rows_list,
+                                                      int32_t *slow_list, unsigned long long *counters)
+{
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chains) return;
+    const KbChainRec c = chains[ci];
+    const KbGroupInfo gi = ginfo[c.group];
+    const uint64_t *ax = cx + gi.a_base;
+    uint64_t *ay = cy + gi.a_base;
+    int32_t *K = kscratch + gi.a_base + c.as;  // the chain's own anchors index a private stretch of the scratch
+    KbPlan pl;
+    KbJobCount count;
+    int nj = kb_stage_plan(ix, bt, gi.asm_id, gi.gene, c.as, c.cnt, c.mlen, gi.n_a, ax, ay, K, pl, count);
+    long long base = -1;
+    if (nj >= 0) {
+        base = (long long)atomicAdd(&counters[KB_SC_JOBS], (unsigned long long)nj);
+        if (base + nj > job_cap) nj = -1;
+    }
+    if (nj < 0) {
+        pl.ok = 0;
+        plans[ci] = pl;
+        slow_list[atomicAdd(&counters[KB_SC_SLOW], 1ull)] = (int32_t)ci;
+        return;
+    }
+    KbJobWrite write{jobs + base, (int32_t)ci};
+    kb_stage_plan(ix, bt, gi.asm_id, gi.gene, c.as, c.cnt, c.mlen, gi.n_a, ax, ay, K, pl, write);
+    pl.job_base = base;
+    plans[ci] = pl;
+    for (int k = 0; k < nj; ++k) {
+        const KbJob &J = jobs[base + k];
+        const bool band = J.kind == KB_JOB_FILL && J.qlen + J.tlen <= 8184 && kb_band_eligible(ix.p.max_sw_cells, J.qlen, J.tlen, J.w, J.flag);
+        if (band) band_list[atomicAdd(&counters[KB_SC_BAND], 1ull)] = (int32_t)(base + k);
+        else rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = (int32_t)(base + k);
+    }
+}
+
+// results of one DP job -> its record, CIGAR into the job pool (all lanes copy)
+static __device__ __forceinline__ void kb_job_finish(int lane, KbJob *J, const KbEz &ez, const uint32_t *ezcig, uint32_t *jobcig,
+                                                     int64_t jobcig_cap, unsigned long long *counters)
+{
+    int n = ez.n_cigar;
+    unsigned long long off = 0;
+    if (lane == 0 && n > 0) off = atomicAdd(&counters[KB_SC_JOBCIG], (unsigned long long)n);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (n > 0) {
+        if ((int64_t)(off + n) > jobcig_cap) n = -2;  // no room: the chain goes to kb_align1
+        else
+            for (int i = lane; i < n; i += 32) jobcig[off + i] = ezcig[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        J->score = ez.score, J->max = ez.max, J->max_t = ez.max_t, J->max_q = ez.max_q, J->zdropped = ez.zdropped;
+        J->n_cigar = n, J->cigar_off = (int64_t)off, J->state = 1;
+    }
+}
+
+// certified band pass over the gap fills: one warp per job, persistent, dynamic queue
+__global__ void __launch_bounds__(128, 4) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, int32_t *rows_list,
+                                                        uint8_t *scratch, size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
+                                                        unsigned long long *counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    KbAlignScratch S;
+    memset(&S, 0, sizeof(S));
+    S.ezcig = reinterpret_cast<uint32_t *>(scratch + (size_t)wg * scratch_bytes);
+    S.tb = reinterpret_cast<uint8_t *>(S.ezcig + KB_CIG_MAX);
+    const KbDpConst P = kb_dp_const(ix.p);
+    const long long n = (long long)counters[KB_SC_BAND];
+    int64_t cells = 0;
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&counters[KB_SC_QBAND], 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if ((long long)k >= n) break;
+        const int jid = band_list[k];
+        KbJob *J = jobs + jid;
+        const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff, 1};
+        const KbDirPack st{bt.seq2, bt.nmask, J->tpos, 1};
+        KbEz ez;
+        const int ok = kb_global_band(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
+        if (lane == 0) KB_DP_STAT(0, ok ? 0 : 1, (int64_t)32 * (J->qlen + J->tlen + 1));
+        if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
+        else if (lane == 0) rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
+    }
+    if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
+}
+
+// row-stripe wavefront over everything else (end extensions, fills the band pass could not certify)
+__global__ void __launch_bounds__(128, 4) kb_rows_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *rows_list, uint8_t *scratch,
+                                                        size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
+                                                        unsigned long long *counters)
+{
+    __shared__ uint32_t wmax_ring[4][512];
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
+    S.wmax = wmax_ring[threadIdx.x >> 5];
+    for (int x = lane; x < 512; x += 32) S.wmax[x] = 0;
+    __syncwarp();
+    const KbDpConst P = kb_dp_const(ix.p);
+    const long long n = (long long)counters[KB_SC_ROWS];
+    int64_t cells = 0;
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&counters[KB_SC_QROWS], 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if ((long long)k >= n) break;
+        KbJob *J = jobs + rows_list[k];
+        const int dir = J->kind == KB_JOB_LEFT ? -1 : 1;
+        const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff + (dir < 0 ? -1 : 0), dir};
+        const KbDirPack st{bt.seq2, bt.nmask, J->tpos + (dir < 0 ? -1 : 0), dir};
+        KbEz ez;
+        const bool track = !(J->flag & KB_EZ_GLOBAL_NO_ZDROP);
+        if (lane == 0) KB_DP_STAT(track ? 1 : 0, J->tlen > 256 ? 3 : 2, (int64_t)J->qlen * J->tlen);
+        if (track) kb_rows<true>(P, lane, J->qlen, sq, J->tlen, st, J->w, J->zdrop, J->flag, ez, S, &cells);
+        else kb_rows<false>(P, lane, J->qlen, sq, J->tlen, st, J->w, J->zdrop, J->flag, ez, S, &cells);
+        kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
+    }
+    if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
+}
+
+// one thread per planned chain: concatenate, test, mm_update_extra, emit the raw hit
+__global__ void __launch_bounds__(128) kb_assemble_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
+                                                          const KbGroupInfo *ginfo, const KbPlan *plans, const KbJob *jobs,
+                                                          const uint32_t *jobcig, uint32_t *tmpcig, int64_t tmpcig_cap, KbRawHit *raw,
+                                                          int64_t raw_cap, uint32_t *pool, int64_t pool_cap, int32_t *slow_list,
+                                                          unsigned long long *counters)
+{
+    const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chains) return;
+    const KbPlan pl = plans[ci];
+    if (!pl.ok) return;
+    const KbChainRec c = chains[ci];
+    const KbGroupInfo gi = ginfo[c.group];
+    const KbJob *J = jobs + pl.job_base;
+    long long total = 0;
+    for (int k = 0; k < pl.n_jobs; ++k) total += J[k].n_cigar > 0 ? J[k].n_cigar : 0;
+    const long long toff = (long long)atomicAdd(&counters[KB_SC_TMPCIG], (unsigned long long)(total + 1));
+    KbReg r;
+    const int reg_idx = (int)(ci - gi.chain_base);
+    r.as = c.as, r.cnt = c.cnt, r.score = c.score, r.score0 = c.score0, r.mlen = c.mlen, r.blen = c.blen, r.parent = c.parent, r.id = reg_idx;
+    r.hash = c.hash, r.rev = c.rev, r.rid = c.rid, r.rs = c.rs, r.re = c.re, r.qs = c.qs, r.qe = c.qe;
+    r.has_p = 0, r.dp_score = 0, r.dp_max = 0, r.n_ambi = 0, r.n_cigar = 0;
+    int rc = -1;
+    if (toff + total + 1 <= tmpcig_cap) rc = kb_stage_assemble(ix, bt, gi.gene, pl, J, jobcig, r, tmpcig + toff);
+    if (rc != 0) {
+        slow_list[atomicAdd(&counters[KB_SC_SLOW], 1ull)] = (int32_t)ci;
+        return;
+    }
+    const int ncg = r.n_cigar;
+    const unsigned long long slot = atomicAdd(&counters[4], 1ull);
+    const unsigned long long coff = atomicAdd(&counters[5], (unsigned long long)ncg);
+    if ((int64_t)slot < raw_cap) {
+        KbRawHit h;
+        h.group = c.group, h.reg_idx = reg_idx, h.split_idx = 0;
+        h.cnt = r.cnt, h.score = r.score, h.score0 = r.score0, h.hash = r.hash;
+        h.rev = r.rev, h.rid = r.rid, h.rs = r.rs, h.re = r.re, h.qs = r.qs, h.qe = r.qe;
+        h.has_p = r.has_p, h.dp_score = r.dp_score, h.dp_max = r.dp_max, h.dp_max2 = 0, h.n_ambi = r.n_ambi, h.mlen = r.mlen, h.blen = r.blen;
+        h.parent = r.parent, h.subsc = c.subsc, h.n_sub = c.n_sub, h.mapq = 0, h.n_cigar = ncg, h.cigar_off = (int64_t)coff;
+        h.err = 0, h.pad = 0;
+        raw[slot] = h;
+    }
+    if ((int64_t)(coff + ncg) <= pool_cap)
+        for (int i = 0; i < ncg; ++i) pool[coff + i] = tmpcig[toff + i];
+}
+
+size_t kb_band_scratch_bytes() { return (size_t)KB_CIG_MAX * 4 + 32 * 8200 + 256; }
+size_t kb_sizeof_job() { return sizeof(KbJob); }
+size_t kb_sizeof_plan() { return sizeof(KbPlan); }
+
+void kb_launch_stage_plan(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
+                          const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, int64_t job_cap, int32_t *band_list,
+                          int32_t *rows_list, int32_t *slow_list, unsigned long long *counters, cudaStream_t st)
+{
+    if (n_chains <= 0) return;
+    kb_plan_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, kscratch, (KbPlan *)plans,
+                                                                       (KbJob *)jobs, job_cap, band_list, rows_list, slow_list, counters);
+}
+void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, uint8_t *band_scratch,
+                        int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
+                        unsigned long long *counters, cudaStream_t st)
+{
+    kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, rows_list, band_scratch, kb_band_scratch_bytes(),
+                                                               jobcig, jobcig_cap, counters);
+    kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, rows_list, rows_scratch, rows_scratch_bytes, jobcig,
+                                                               jobcig_cap, counters);
+}
+void kb_launch_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
+                              const void *plans, const void *jobs, const uint32_t *jobcig, uint32_t *tmpcig, int64_t tmpcig_cap, KbRawHit *raw,
+                              int64_t raw_cap, uint32_t *pool, int64_t pool_cap, int32_t *slow_list, unsigned long long *counters,
+                              cudaStream_t st)
+{
+    if (n_chains <= 0) return;
+    kb_assemble_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, (const KbPlan *)plans,
+                                                                           (const KbJob *)jobs, jobcig, tmpcig, tmpcig_cap, raw, raw_cap, pool,
+                                                                           pool_cap, slow_list, counters);
 }
 
 // ------------------------------------------------------------------ finalisation

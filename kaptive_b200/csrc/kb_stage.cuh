@@ -61,12 +61,13 @@ struct KbPackSeq {
     KB_HD KbPackSeq operator+(int d) const { return KbPackSeq{seq2, nmask, pos + d}; }
 };
 
-// Plan one chain.  `K` is int32 scratch for the seed filters (>= cnt entries).  jobs[] receives at most
-// KB_JOBS_PER_CHAIN_MAX jobs (chain / job_base are filled in by the caller).  Returns the number of jobs, or -1 when
-// the chain has to take the kb_align1 path.  The seed-filter flags written into ay[] are the ones kb_align1 would
-// write (idempotent), so a chain can be planned first and still be handed to kb_align1 afterwards.
+// Plan one chain.  `K` is int32 scratch for the seed filters (>= cnt entries).  Every DP job is handed to
+// sink(job) -> bool (false = no room); chain / job_base are the caller's business.  Returns the number of jobs, or -1
+// when the chain has to take the kb_align1 path.  The seed-filter flags written into ay[] are the ones kb_align1
+// would write (idempotent), so a chain can be planned twice (count, then emit) and still be handed to kb_align1.
+template <class Sink>
 KB_HD int kb_stage_plan(const KbIndexView &ix, const KbBatchView &bt, int asm_id, int gene, int r_as, int r_cnt, int r_mlen, int n_a,
-                        const uint64_t *ax, uint64_t *ay, int32_t *K, KbPlan &pl, KbJob *jobs)
+                        const uint64_t *ax, uint64_t *ay, int32_t *K, KbPlan &pl, Sink &sink)
 {
     const kb_params_t &P = ix.p;
     const int hk = P.k >> 1;
@@ -88,10 +89,12 @@ KB_HD int kb_stage_plan(const KbIndexView &ix, const KbBatchView &bt, int asm_id
         if (nj >= KB_JOBS_PER_CHAIN_MAX) return false;
         const bool track = !(flag & KB_EZ_GLOBAL_NO_ZDROP);
         if (!kb_rows_eligible(P.max_sw_cells, qlen, tlen, w, track)) return false;
-        KbJob &j = jobs[nj++];
-        j.kind = kind, j.qoff = qoff, j.qlen = qlen, j.tlen = tlen, j.w = w, j.zdrop = zdrop, j.flag = flag;
+        KbJob j;
+        j.chain = -1, j.kind = kind, j.qoff = qoff, j.qlen = qlen, j.tlen = tlen, j.w = w, j.zdrop = zdrop, j.flag = flag;
         j.tpos = tpos, j.qbase = qbase, j.qrev = W.rev;
         j.score = KB_NEG_INF, j.max = 0, j.max_t = j.max_q = -1, j.zdropped = 0, j.n_cigar = 0, j.state = 0, j.cigar_off = 0;
+        if (!sink(nj, j)) return false;
+        ++nj;
         return true;
     };
     int32_t rs = W.rs, qs = W.qs;
@@ -117,6 +120,19 @@ KB_HD int kb_stage_plan(const KbIndexView &ix, const KbBatchView &bt, int asm_id
     pl.ok = 1, pl.n_jobs = nj;
     return nj;
 }
+struct KbJobCount {  // sink that only counts
+    KB_HD bool operator()(int, const KbJob &) { return true; }
+};
+struct KbJobWrite {  // sink that stores job k at out[k]
+    KbJob *out;
+    int32_t chain;
+    KB_HD bool operator()(int k, const KbJob &j)
+    {
+        out[k] = j;
+        out[k].chain = chain;
+        return true;
+    }
+};
 
 // Assemble one planned chain from its finished jobs.  `cig` is scratch for the chain's CIGAR (>= the sum of the jobs'
 // n_cigar, at most KB_CIG_MAX are used), `jobcig` the pool the DP kernels wrote the per-job CIGARs to.  Returns 0

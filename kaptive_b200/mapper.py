@@ -213,7 +213,7 @@ def _drain(L, r, n_asm: int, fetch: bool) -> MapResult:
     if n.value:
         chains = np.zeros((n.value, 10), dtype=np.int32)
         check(L.kb_result_fetch_chains(r, ptr(chains), n.value, C.byref(n)))
-    names = ("minimizers", "anchors", "groups", "chains", "raw_hits", "launches", "dp_cells", "_")
+    names = ("minimizers", "anchors", "groups", "chains", "raw_hits", "launches", "dp_cells", "slow_chains")
     return MapResult(
         hits=hits,
         cigar=cigar,

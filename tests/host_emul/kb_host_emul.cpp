@@ -214,8 +214,13 @@ EmuResult *kbe_map_assembly(void *idx_, const uint8_t *ascii, const int64_t *ctg
             KbPlan pl;
             std::vector<KbJob> jobs(KB_JOBS_PER_CHAIN_MAX);
             std::vector<int32_t> K((size_t)gi.n_a + 8);
+            KbJobCount count;
+            KbJobWrite write{jobs.data(), (int32_t)ci};
             int nj = kb_stage_plan(ix, bt, gi.asm_id, gi.gene, r.as, r.cnt, r.mlen, gi.n_a, cx.data() + gi.a_base, cy.data() + gi.a_base,
-                                   K.data(), pl, jobs.data());
+                                   K.data(), pl, count);
+            if (nj >= 0)
+                nj = kb_stage_plan(ix, bt, gi.asm_id, gi.gene, r.as, r.cnt, r.mlen, gi.n_a, cx.data() + gi.a_base, cy.data() + gi.a_base,
+                                   K.data(), pl, write);
             if (nj >= 0) {
                 std::vector<uint32_t> jobcig;
                 const uint8_t *gq = c.rev ? ix.gseq_rev : ix.gseq_fwd;
