@@ -273,11 +273,13 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else {}
     L.kb_debug_dp_stats(ptr(dp_raw), 0)
     dp_stats = {}
-    for ki, kind in enumerate(("fill", "ext", "fill_zdrop")):
+    for ki, kind in enumerate(("fill", "ext", "fill_wide")):
         for pi, path in enumerate(("band_ok", "band_rejected", "reg", "reg_tiled", "scratch")):
             c, n = int(dp_raw[2 * (5 * ki + pi)]), int(dp_raw[2 * (5 * ki + pi) + 1])
             if c:
                 dp_stats[f"{kind}/{path}"] = {"calls": c // a.steps, "cells": n // a.steps}
+    if dp_raw[30]:
+        dp_stats["ext/zdropped"] = {"calls": int(dp_raw[30]) // a.steps, "mean_break_permille": int(dp_raw[31] // dp_raw[30])}
     dev_ms = stage_acc.get("total", 0.0) / a.steps
     t = torch.tensor([wall, dev_ms], device=dev, dtype=torch.float64)
     if dist:

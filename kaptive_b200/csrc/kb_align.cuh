@@ -309,6 +309,7 @@ KB_HD bool kb_band_eligible(int64_t max_sw_cells, int qlen, int tlen, int w, int
 
 #ifndef KB_DP_STAT
 #define KB_DP_STAT(kind, path, cells) ((void)0)
+#define KB_DP_STAT_RAW(slot, v) ((void)0)
 #endif
 #ifdef __CUDACC__
 #define kb_backtrack_lane0(lane, qlen, tlen, flag, ez, S) kb_backtrack<32>(lane, qlen, tlen, flag, ez, S)

@@ -244,6 +244,7 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
     const int d1 = tlen - qlen, lo_d = d1 < 0 ? d1 : 0, hi_d = d1 > 0 ? d1 : 0;
     const int margin = (63 - (hi_d - lo_d)) >> 1;
     const int r_end = tlen + qlen;  // last anti-diagonal in shifted coordinates: the cell (tlen, qlen)
+    ez.score = KB_NEG_INF;
     if (margin < KB_BAND_MIN_MARGIN || (int64_t)32 * (r_end + 8) > P.max_sw_cells) return 0;
     const KbC8 c = kb_c8(P, 0);
     const int dlo = lo_d - margin, dhi = dlo + 63;
@@ -292,7 +293,10 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
         const int D_hi = dhi + 1, I_hi = D_hi - d1, I_lo = 1 - dlo, D_lo = I_lo + d1;
         int b_hi = (tlen - D_hi < 0 || qlen - I_hi < 0) ? KB_NEG_INF : P.a * (tlen - D_hi) - kb_gapcost2(P, D_hi) - kb_gapcost2(P, I_hi);
         int b_lo = (tlen - D_lo < 0 || qlen - I_lo < 0) ? KB_NEG_INF : P.a * (tlen - D_lo) - kb_gapcost2(P, D_lo) - kb_gapcost2(P, I_lo);
-        if (!(score > (b_hi > b_lo ? b_hi : b_lo))) return 0;
+        if (!(score > (b_hi > b_lo ? b_hi : b_lo))) {
+            ez.score = score;  // a valid alignment's score all the same: a lower bound for any wider band
+            return 0;
+        }
     }
     __syncwarp();
     int bad = 0;
@@ -303,6 +307,143 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
             return 0xffu;
         }
         return (kb_ld_u32(tbw + (r2 >> 2) * 32 + l) >> ((r2 & 3) * 8)) & 0xffu;
+    });
+    if (__any_sync(0xffffffffu, bad)) return 0;
+    ez.max = 0, ez.max_q = ez.max_t = -1, ez.zdropped = 0;
+    ez.score = score, ez.n_cigar = n_cigar;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Wider certified bands: the same sliding window with K cells per lane (64 K diagonals, K = 2 or 4), for gap fills
+// whose 64-diagonal pass scored too low to certify itself.  Lane l holds the K consecutive cells l K .. l K + K - 1
+// of the window, so on an "A" step only slot 0 needs a shuffle (cell c - 1 lives in the lane's own slot m - 1) and on
+// a "B" step only slot K - 1 does.  The target / query bases ride through the window like a systolic array: a B step
+// moves every target base one cell down (the top cell of lane 31 loads the new one), an A step moves every query
+// base one cell up.  kb_band_bound gives the certificate threshold for a window of K slots, so the caller can pick
+// the smallest K the first pass's score (a lower bound of every wider pass's score) already certifies.
+__device__ __forceinline__ bool kb_band_geometry(int qlen, int tlen, int K, int &dlo, int &dhi)
+{
+    const int d1 = tlen - qlen, lo_d = d1 < 0 ? d1 : 0, hi_d = d1 > 0 ? d1 : 0;
+    const int margin = (64 * K - 1 - (hi_d - lo_d)) >> 1;
+    dlo = lo_d - margin, dhi = dlo + 64 * K - 1;
+    return margin >= KB_BAND_MIN_MARGIN;
+}
+// any path leaving the band [dlo, dhi] scores at most this
+__device__ __forceinline__ int kb_band_bound(const KbDpConst &P, int qlen, int tlen, int dlo, int dhi)
+{
+    const int d1 = tlen - qlen;
+    const int D_hi = dhi + 1, I_hi = D_hi - d1, I_lo = 1 - dlo, D_lo = I_lo + d1;
+    const int b_hi = (tlen - D_hi < 0 || qlen - I_hi < 0) ? KB_NEG_INF : P.a * (tlen - D_hi) - kb_gapcost2(P, D_hi) - kb_gapcost2(P, I_hi);
+    const int b_lo = (tlen - D_lo < 0 || qlen - I_lo < 0) ? KB_NEG_INF : P.a * (tlen - D_lo) - kb_gapcost2(P, D_lo) - kb_gapcost2(P, I_lo);
+    return b_hi > b_lo ? b_hi : b_lo;
+}
+
+template <int K, class SQ, class ST>
+static __device__ __noinline__ int kb_global_bandK(const KbDpConst P, int lane, int qlen, const SQ qs, int tlen, const ST ts, int flag, KbEz &ez,
+                                                   const KbAlignScratch S, int64_t *cell_counter)
+{
+    int dlo, dhi;
+    const int r_end = tlen + qlen;
+    if (!kb_band_geometry(qlen, tlen, K, dlo, dhi) || (int64_t)32 * K * (r_end + 8) > P.max_sw_cells) return 0;
+    const KbC8 c = kb_c8(P, 0);
+    uint8_t *tb = S.tb;  // [r'][lane][K]
+    int32_t H1[K], H2[K], E1[K], E2[K], F1[K], F2[K];
+    uint32_t srow[K], sel[K];
+#pragma unroll
+    for (int m = 0; m < K; ++m) H1[m] = H2[m] = E1[m] = E2[m] = F1[m] = F2[m] = KB_NEG8, srow[m] = sel[m] = 0;
+    const int T0 = (dlo + 1) >> 1;  // T(0)
+    int tp0 = T0 + lane * K, jp0 = -tp0;  // t', j' of the lane's slot 0 on anti-diagonal 0 (slot m: tp0 + m, jp0 - m)
+    auto tbase = [&](int tp) { return kb_score_row(P, c, ts((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1))); };
+    auto qbase = [&](int jp) { return kb_score_sel(qs((jp < 1 ? 0 : (jp > qlen ? qlen : jp) - 1))); };
+#pragma unroll
+    for (int m = 0; m < K; ++m) srow[m] = tbase(tp0 + m), sel[m] = qbase(jp0 - m);
+    const int r_edge = (-dlo > dhi ? -dlo : dhi) + 1;  // boundary cells can occur up to here
+    for (int rp = 0; rp <= r_end; ++rp) {
+        const bool stepB = (rp + dlo) & 1;
+        const bool edge = rp <= r_edge;
+        uint32_t tbw = 0;
+        if (rp > 0) {
+            if (stepB) {  // every cell moves one target base on; slot K-1 takes the next lane's slot 0
+                ++tp0;
+                uint32_t nx = __shfl_down_sync(0xffffffffu, srow[0], 1);
+                if (lane == 31) nx = tbase(tp0 + K - 1);
+#pragma unroll
+                for (int m = 0; m + 1 < K; ++m) srow[m] = srow[m + 1];
+                srow[K - 1] = nx;
+            } else {  // every cell moves one query base on; slot 0 takes the previous lane's slot K-1
+                ++jp0;
+                uint32_t nx = __shfl_up_sync(0xffffffffu, sel[K - 1], 1);
+                if (lane == 0) nx = qbase(jp0);
+#pragma unroll
+                for (int m = K - 1; m > 0; --m) sel[m] = sel[m - 1];
+                sel[0] = nx;
+            }
+        }
+        if (!stepB) {  // A: (t-1, j) is cell c - 1; descending so that slot m reads slot m - 1 before it is overwritten
+            int32_t uH = __shfl_up_sync(0xffffffffu, H1[K - 1], 1), uE1 = __shfl_up_sync(0xffffffffu, E1[K - 1], 1),
+                    uE2 = __shfl_up_sync(0xffffffffu, E2[K - 1], 1);
+            if (lane == 0) uH = uE1 = uE2 = KB_NEG8;
+#pragma unroll
+            for (int m = K - 1; m >= 0; --m) {
+                const int32_t hu = m > 0 ? H1[m > 0 ? m - 1 : 0] : uH;
+                int32_t e1 = m > 0 ? E1[m > 0 ? m - 1 : 0] : uE1, e2 = m > 0 ? E2[m > 0 ? m - 1 : 0] : uE2;
+                uint32_t d;
+                int32_t z = kb_cell8(c, hu, e1, e2, H1[m], F1[m], F2[m], H2[m], srow[m], sel[m], d);
+                if (edge) {
+                    const int tp = tp0 + m, jp = jp0 - m;
+                    if (tp <= 0 || jp <= 0) {
+                        const int mm = tp > jp ? tp : jp;
+                        z = (tp < 0 || jp < 0) ? KB_NEG8 : (mm == 0 ? 0 : -8 * kb_gapcost2(P, mm));
+                        e1 = e2 = F1[m] = F2[m] = KB_NEG8, d = 0;
+                    }
+                }
+                H2[m] = H1[m], H1[m] = z, E1[m] = e1, E2[m] = e2;
+                tbw |= d << (8 * m);
+            }
+        } else {  // B: (t, j-1) is cell c + 1; ascending
+            int32_t lH = __shfl_down_sync(0xffffffffu, H1[0], 1), lF1 = __shfl_down_sync(0xffffffffu, F1[0], 1),
+                    lF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
+            if (lane == 31) lH = lF1 = lF2 = KB_NEG8;
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const int32_t hl = m + 1 < K ? H1[m + 1 < K ? m + 1 : 0] : lH;
+                int32_t f1 = m + 1 < K ? F1[m + 1 < K ? m + 1 : 0] : lF1, f2 = m + 1 < K ? F2[m + 1 < K ? m + 1 : 0] : lF2;
+                uint32_t d;
+                int32_t z = kb_cell8(c, H1[m], E1[m], E2[m], hl, f1, f2, H2[m], srow[m], sel[m], d);
+                if (edge) {
+                    const int tp = tp0 + m, jp = jp0 - m;
+                    if (tp <= 0 || jp <= 0) {
+                        const int mm = tp > jp ? tp : jp;
+                        z = (tp < 0 || jp < 0) ? KB_NEG8 : (mm == 0 ? 0 : -8 * kb_gapcost2(P, mm));
+                        E1[m] = E2[m] = f1 = f2 = KB_NEG8, d = 0;
+                    }
+                }
+                H2[m] = H1[m], H1[m] = z, F1[m] = f1, F2[m] = f2;
+                tbw |= d << (8 * m);
+            }
+        }
+        uint8_t *dst = tb + ((size_t)rp * 32 + lane) * K;
+        if (K == 4) kb_st_u32(reinterpret_cast<uint32_t *>(dst), tbw);
+        else asm volatile("st.global.u16 [%0], %1;" ::"l"(__cvta_generic_to_global(dst)), "h"((unsigned short)tbw) : "memory");
+    }
+    if (cell_counter && lane == 0) *cell_counter += (int64_t)32 * K * (r_end + 1);
+    const int cend = tlen - ((r_end + dlo + 1) >> 1);  // window index of the cell (tlen, qlen)
+    int32_t hv = H1[0];
+#pragma unroll
+    for (int m = 1; m < K; ++m)
+        if (m == cend % K) hv = H1[m];
+    const int score = __shfl_sync(0xffffffffu, hv, (cend / K) & 31) >> 3;
+    if (!(score > kb_band_bound(P, qlen, tlen, dlo, dhi))) return 0;
+    __syncwarp();
+    int bad = 0;
+    const int n_cigar = kb_backtrack_warp(lane, tlen - 1, qlen - 1, 0, flag, S.ezcig, [&](int i, int j) -> uint32_t {
+        const int r2 = i + j + 2, cc = i + 1 - ((r2 + dlo + 1) >> 1);
+        if ((unsigned)cc >= (unsigned)(32 * K)) {
+            bad = 1;  // cannot happen once certified
+            return 0xffu;
+        }
+        return (uint32_t)kb_ld_u8(tb + (size_t)r2 * 32 * K + cc);
     });
     if (__any_sync(0xffffffffu, bad)) return 0;
     ez.max = 0, ez.max_q = ez.max_t = -1, ez.zdropped = 0;
@@ -485,6 +626,7 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
                     const int tl = max_t - mt, ql = (r - max_t) - mq, l = tl > ql ? tl - ql : ql - tl;
                     if (zdrop >= 0 && mx - max_H > zdrop + l * P.e2) {
                         zd = 1;
+                        KB_DP_STAT_RAW(30, 1), KB_DP_STAT_RAW(31, (int64_t)r * 1000 / n_diag);
                         break;
                     }
                 }

@@ -14,6 +14,7 @@ __device__ unsigned long long g_kb_dp_stats[32];
         atomicAdd(&g_kb_dp_stats[2 * (5 * (kind) + (path))], 1ull);                         \
         atomicAdd(&g_kb_dp_stats[2 * (5 * (kind) + (path)) + 1], (unsigned long long)(cells)); \
     } while (0)
+#define KB_DP_STAT_RAW(slot, v) atomicAdd(&g_kb_dp_stats[slot], (unsigned long long)(v))
 #include "kb_final.cuh"
 #include "kb_stage.cuh"
 #include "kb_kernels.h"
@@ -342,8 +343,19 @@ __global__ void __launch_bounds__(128, 4) kb_band_kernel(KbIndexView ix, KbBatch
         const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff, 1};
         const KbDirPack st{bt.seq2, bt.nmask, J->tpos, 1};
         KbEz ez;
-        const int ok = kb_global_band(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
+        int ok = kb_global_band(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
         if (lane == 0) KB_DP_STAT(0, ok ? 0 : 1, (int64_t)32 * (J->qlen + J->tlen + 1));
+        if (!ok && ez.score > KB_NEG_INF) {  // the smallest wider band this score already certifies, if any
+            int dlo, dhi, k2 = 0;
+            if (kb_band_geometry(J->qlen, J->tlen, 2, dlo, dhi) && ez.score > kb_band_bound(P, J->qlen, J->tlen, dlo, dhi)) k2 = 2;
+            else if (kb_band_geometry(J->qlen, J->tlen, 4, dlo, dhi) && ez.score > kb_band_bound(P, J->qlen, J->tlen, dlo, dhi)) k2 = 4;
+            // worth it only while the window stays well below the rectangle
+            if (k2 && 64 * k2 * 3 <= 2 * (J->qlen + J->tlen)) {
+                ok = k2 == 2 ? kb_global_bandK<2>(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells)
+                             : kb_global_bandK<4>(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
+                if (lane == 0) KB_DP_STAT(2, ok ? 0 : 1, (int64_t)32 * k2 * (J->qlen + J->tlen + 1));
+            }
+        }
         if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
         else if (lane == 0) rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
     }
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(128) kb_assemble_kernel(KbIndexView ix, KbBatc
         for (int i = 0; i < ncg; ++i) pool[coff + i] = tmpcig[toff + i];
 }
 
-size_t kb_band_scratch_bytes() { return (size_t)KB_CIG_MAX * 4 + 32 * 8200 + 256; }
+size_t kb_band_scratch_bytes() { return (size_t)KB_CIG_MAX * 4 + 4 * 32 * 8200 + 256; }
 size_t kb_sizeof_job() { return sizeof(KbJob); }
 size_t kb_sizeof_plan() { return sizeof(KbPlan); }
 
