@@ -99,6 +99,9 @@ __device__ __forceinline__ KbC8 kb_c8(const KbDpConst &P, int rb)
     c.x1 = 8 * P.e, c.x2 = 8 * P.e2;
     c.th1 = -8 * P.q + (rb ? -1 : 7), c.th2 = -8 * P.q2 + (rb ? -1 : 7);
     c.sN = (uint32_t)(-8 * P.sc_ambi + c.tag_d) & 0xffu;
+    // keep the constants in registers: left alone, ptxas re-derives them from the parameter bank in every cell (two
+    // extra LDC per cell); a value that went through a shuffle is opaque to it
+    c.x1 = __shfl_sync(0xffffffffu, c.x1, 0), c.x2 = __shfl_sync(0xffffffffu, c.x2, 0);
     return c;
 }
 // initial (never winning) values of the tagged gap states
@@ -590,12 +593,13 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
                 if (any_edge) kb_rows_body<true, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
                 else kb_rows_body<false, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
                 oh = hu, oe1 = e1, oe2 = e2;
-                uint32_t *dst = reinterpret_cast<uint32_t *>(tbt + (size_t)s * 256);  // a lane's slot is 8 bytes wide whatever kact is
+                uint32_t *dst = reinterpret_cast<uint32_t *>(tbt);  // a lane's slot is 8 bytes wide whatever kact is
                 kb_st_u32(dst + 1, tbw[1]);
                 if (kact > 4) kb_st_u32(dst, tbw[0]);
                 if (spill && lane == 31) kb_st_s32(eout + j, oh), kb_st_s32(eout + KB_DP_MAXLEN + j, oe1), kb_st_s32(eout + 2 * KB_DP_MAXLEN + j, oe2);
             }
             dg = uh;
+            tbt += 256;
             if (TRACK && (s & 255) == 255) drain(T0 + s - 287);
         }
         if (TRACK) drain(T0 + nstep - 288), drain(T0 + nstep + 224);

@@ -352,7 +352,7 @@ void kb_result_destroy(kb_result_t *r)
 {
     if (!r) return;
     cudaSetDevice(r->device);
-    for (void *p : r->owned) cudaFree(p);
+    for (void *p : r->owned) cudaFreeAsync(p, 0);  // stream-ordered pool memory: back to the pool without a device-wide sync
     delete r;
 }
 
@@ -551,7 +551,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             CU(cudaMemcpyAsync(&last_n, nseed + n_groups - 1, 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             R->n_anchor_dump = last_off + last_n;
-            CU(cudaMalloc((void **)&R->d_anchor_dump, (size_t)(R->n_anchor_dump + 1) * 7 * 4));
+            CU(cudaMallocAsync((void **)&R->d_anchor_dump, (size_t)(R->n_anchor_dump + 1) * 7 * 4, st));
             R->owned.push_back(R->d_anchor_dump);
             kb_launch_dump_anchors(bv, ginfo, n_groups, gstart, W.x, W.y, aoff, R->d_anchor_dump, st);
             std::vector<KbChainRec> hch((size_t)n_chains);
@@ -603,7 +603,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             band_scratch = P.get<uint8_t>((size_t)band_warps * kb_band_scratch_bytes());
         }
         for (int attempt = 0;; ++attempt) {
-            CU(cudaMalloc((void **)&pool, (size_t)pool_cap * 4 + 16));
+            CU(cudaMallocAsync((void **)&pool, (size_t)pool_cap * 4 + 16, st));
             CU(cudaMemsetAsync(d_next, 0, 8, st));
             CU(cudaMemsetAsync(d_counters + 4, 0, 16, st));
             CU(cudaMemsetAsync(d_counters + 8, 0, 8 * 8, st));
@@ -630,7 +630,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             if (n_pool <= pool_cap) break;
             if (attempt >= 1) throw std::string("cigar pool overflow");
             // NB: the seed-filter flags written into cy[] are idempotent, so the stage can simply be re-run
-            CU(cudaFree(pool));
+            CU(cudaFreeAsync(pool, st));
             pool_cap = n_pool + 1024;
         }
         R->pool = pool, R->owned.push_back(pool), R->n_cigar = n_pool;
@@ -672,19 +672,23 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         R->n_hits = n_hits;
         {
             size_t n = (size_t)n_hits + 1;
+            // one stream-ordered allocation for the 17 result arrays (256-byte aligned slices)
+            const size_t n4 = (n * 4 + 255) & ~(size_t)255, n1 = (n + 255) & ~(size_t)255, n8 = (n * 8 + 255) & ~(size_t)255;
+            uint8_t *arena = nullptr;
+            CU(cudaMallocAsync((void **)&arena, 13 * n4 + 3 * n1 + n8, st));
+            R->owned.push_back(arena);
             auto own = [&](size_t bytes) {
-                void *q = nullptr;
-                CU(cudaMalloc(&q, bytes));
-                R->owned.push_back(q);
+                void *q = arena;
+                arena += bytes;
                 return q;
             };
             kb_hits_t &d = R->d;
             d.capacity = n_hits;
-            d.asm_id = (int32_t *)own(n * 4), d.gene = (int32_t *)own(n * 4), d.q_start = (int32_t *)own(n * 4), d.q_end = (int32_t *)own(n * 4);
-            d.t_ctg = (int32_t *)own(n * 4), d.t_len = (int32_t *)own(n * 4), d.t_start = (int32_t *)own(n * 4), d.t_end = (int32_t *)own(n * 4);
-            d.strand = (int8_t *)own(n), d.score = (int32_t *)own(n * 4), d.matches = (int32_t *)own(n * 4), d.block_len = (int32_t *)own(n * 4);
-            d.edit_distance = (int32_t *)own(n * 4), d.mapq = (uint8_t *)own(n), d.is_primary = (uint8_t *)own(n);
-            d.cigar_off = (int64_t *)own(n * 8), d.n_cigar = (int32_t *)own(n * 4);
+            d.asm_id = (int32_t *)own(n4), d.gene = (int32_t *)own(n4), d.q_start = (int32_t *)own(n4), d.q_end = (int32_t *)own(n4);
+            d.t_ctg = (int32_t *)own(n4), d.t_len = (int32_t *)own(n4), d.t_start = (int32_t *)own(n4), d.t_end = (int32_t *)own(n4);
+            d.strand = (int8_t *)own(n1), d.score = (int32_t *)own(n4), d.matches = (int32_t *)own(n4), d.block_len = (int32_t *)own(n4);
+            d.edit_distance = (int32_t *)own(n4), d.mapq = (uint8_t *)own(n1), d.is_primary = (uint8_t *)own(n1);
+            d.cigar_off = (int64_t *)own(n8), d.n_cigar = (int32_t *)own(n4);
             kb_launch_scatter(sorted, keep, oidx, n_raw, ginfo, bv, d, st);
             ++launches;
             CU(cudaGetLastError());
