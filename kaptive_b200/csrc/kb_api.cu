@@ -164,6 +164,16 @@ static int index_upload(kb_index *ix, int device)
         size_t o_gn = put_blob(blob, h.gene_nmin), o_gmo = put_blob(blob, h.gene_min_off), o_gq = put_blob(blob, h.gm_qpos_z);
         size_t o_go = put_blob(blob, h.gm_qocc), o_gh = put_blob(blob, h.gene_hash), o_gso = put_blob(blob, h.gene_seq_off);
         size_t o_f = put_blob(blob, h.gseq_fwd), o_r = put_blob(blob, h.gseq_rev);
+        // presence bitmap over the low hash bits (>= 32 bits per distinct minimizer, at least 2 MB): the scan asks it first
+        uint32_t bbits = 1u << 24;
+        while ((uint64_t)bbits < (uint64_t)h.ht.size() * 16 && bbits < (1u << 30)) bbits <<= 1;
+        std::vector<uint32_t> bloom(bbits / 32, 0);
+        for (uint64_t e : h.ht)
+            if (e) {
+                uint32_t hv = (uint32_t)(e >> KB_HT_KEY_SHIFT) & (bbits - 1);
+                bloom[hv >> 5] |= 1u << (hv & 31);
+            }
+        size_t o_bl = put_blob(blob, bloom);
         CU(cudaMalloc((void **)&ix->d_blob, blob.size()));
         CU(cudaMemcpy(ix->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
         KbIndexView &v = ix->view;
@@ -173,6 +183,7 @@ static int index_upload(kb_index *ix, int device)
         v.gene_nmin = (const int32_t *)(b + o_gn), v.gene_min_off = (const int64_t *)(b + o_gmo), v.gm_qpos_z = (const uint32_t *)(b + o_gq);
         v.gm_qocc = (const int32_t *)(b + o_go), v.gene_hash = (const uint32_t *)(b + o_gh), v.gene_seq_off = (const int64_t *)(b + o_gso);
         v.gseq_fwd = b + o_f, v.gseq_rev = b + o_r;
+        v.bloom = (const uint32_t *)(b + o_bl), v.bloom_mask = bbits - 1;
         ix->device = device;
     } catch (const std::string &e) {
         return fail(KB_ERR_CUDA, e);

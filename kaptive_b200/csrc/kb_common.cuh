@@ -226,6 +226,8 @@ struct KbIndexView {
     const int64_t *gene_seq_off; // into gseq_fwd / gseq_rev
     const uint8_t *gseq_fwd;     // nt4 codes, 1 byte per base
     const uint8_t *gseq_rev;     // reverse complement
+    const uint32_t *bloom;       // device only: 1 bit per (hash & bloom_mask), set for every indexed minimizer
+    uint32_t bloom_mask;
 };
 
 struct KbBatchView {

@@ -154,6 +154,7 @@ KbIndexView KbHostIndex::host_view() const
     v.gene_len = gene_len.data(), v.gene_nmin = gene_nmin.data(), v.gene_min_off = gene_min_off.data();
     v.gm_qpos_z = gm_qpos_z.data(), v.gm_qocc = gm_qocc.data(), v.gene_hash = gene_hash.data();
     v.gene_seq_off = gene_seq_off.data(), v.gseq_fwd = gseq_fwd.data(), v.gseq_rev = gseq_rev.data();
+    v.bloom = nullptr, v.bloom_mask = 0;
     return v;
 }
 
