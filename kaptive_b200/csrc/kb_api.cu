@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,20 +72,67 @@ static int fail(int code, const std::string &msg)
         }                                                                                             \
     } while (0)
 
-struct DevPool {  // frees everything it handed out, in reverse order, on the owning stream
+// Workspace arenas: one big device allocation per concurrent mapping call, kept for the life of the process and handed
+// out by bumping a pointer, so a steady-state call never reaches the CUDA allocator (whose latency is anything between
+// microseconds and a fraction of a second once pools grow or trim).  A call that needs more than its arena holds falls
+// back to cudaMallocAsync for the excess and the arena is regrown when the call returns it.
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t cap = 0, off = 0, demand = 0;
+    int device = 0;
+};
+static std::mutex g_arena_mu;
+static std::vector<Arena *> g_arenas;  // idle arenas
+static Arena *arena_acquire(int device)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_arenas.size(); ++i)
+        if (g_arenas[(size_t)i]->device == device && (best < 0 || g_arenas[(size_t)i]->cap > g_arenas[(size_t)best]->cap)) best = i;
+    Arena *a;
+    if (best >= 0) a = g_arenas[(size_t)best], g_arenas.erase(g_arenas.begin() + best);
+    else a = new Arena(), a->device = device;
+    a->off = a->demand = 0;
+    return a;
+}
+static void arena_release(Arena *a)  // the caller has synchronised the stream that used it
+{
+    if (!a) return;
+    if (a->demand > a->cap) {
+        if (a->base) cudaFree(a->base);
+        a->base = nullptr, a->cap = 0;
+        size_t want = a->demand + a->demand / 8 + (64u << 20);
+        if (cudaMalloc((void **)&a->base, want) == cudaSuccess) a->cap = want;
+        else (void)cudaGetLastError();  // stay on the stream-ordered allocator
+    }
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    g_arenas.push_back(a);
+}
+
+struct DevPool {  // per-call scratch: bump allocation from an arena when it has one, stream-ordered allocations otherwise
     cudaStream_t st = nullptr;
-    std::vector<void *> ptrs;
+    Arena *arena = nullptr;
+    std::vector<void *> ptrs;  // stream-ordered allocations to free
     template <class T>
     T *get(size_t n)
     {
         void *p = nullptr;
         size_t bytes = n * sizeof(T);
         if (bytes == 0) bytes = 16;
+        if (arena) {
+            const size_t al = (bytes + 255) & ~(size_t)255;
+            arena->demand += al;
+            if (arena->off + al <= arena->cap) {
+                p = arena->base + arena->off;
+                arena->off += al;
+                return (T *)p;
+            }
+        }
         CU(cudaMallocAsync(&p, bytes, st));
         ptrs.push_back(p);
         return (T *)p;
     }
-    void release(void *p)
+    void release(void *p)  // arena memory simply stays put until the call ends
     {
         for (size_t i = 0; i < ptrs.size(); ++i)
             if (ptrs[i] == p) {
@@ -289,10 +339,12 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         size_t o_vs = put_blob(blob, L.ctg_vstart), o_acs = put_blob(blob, L.asm_ctg_start), o_cc = put_blob(blob, L.chunk_ctg);
         size_t o_cs = put_blob(blob, L.chunk_start), o_off = put_blob(blob, off_v);
         CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        CU(cudaMalloc((void **)&b->d_blob, blob.size()));
+        // stream-ordered allocations: neither creating nor destroying a batch synchronises the device, so batches of
+        // concurrent calls (kb_map_assemblies' slabs) overlap with each other's kernels
+        CU(cudaMallocAsync((void **)&b->d_blob, blob.size(), st));
         CU(cudaMemcpyAsync(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaMalloc((void **)&b->seq2, (size_t)(L.storage_bases >> 4) * 4 + 64));
-        CU(cudaMalloc((void **)&b->nmask, (size_t)(L.storage_bases >> 5) * 4 + 64));
+        CU(cudaMallocAsync((void **)&b->seq2, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
+        CU(cudaMallocAsync((void **)&b->nmask, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
         // lead-in / tail padding groups
         CU(cudaMemsetAsync(b->seq2, 0, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
         CU(cudaMemsetAsync(b->nmask, 0xff, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
@@ -335,10 +387,10 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         CU(cudaStreamSynchronize(st));
         CU(cudaStreamDestroy(st));
     } catch (const std::string &e) {
-        if (st) cudaStreamDestroy(st);
-        if (b->d_blob) cudaFree(b->d_blob);
-        if (b->seq2) cudaFree(b->seq2);
-        if (b->nmask) cudaFree(b->nmask);
+        if (st) cudaStreamSynchronize(st), cudaStreamDestroy(st);
+        if (b->d_blob) cudaFreeAsync(b->d_blob, 0);
+        if (b->seq2) cudaFreeAsync(b->seq2, 0);
+        if (b->nmask) cudaFreeAsync(b->nmask, 0);
         delete b;
         return fail(KB_ERR_CUDA, e);
     }
@@ -350,9 +402,9 @@ void kb_batch_destroy(kb_batch_t *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->d_blob) cudaFree(b->d_blob);
-    if (b->seq2) cudaFree(b->seq2);
-    if (b->nmask) cudaFree(b->nmask);
+    if (b->d_blob) cudaFreeAsync(b->d_blob, 0);
+    if (b->seq2) cudaFreeAsync(b->seq2, 0);
+    if (b->nmask) cudaFreeAsync(b->nmask, 0);
     delete b;
 }
 int32_t kb_batch_n_assemblies(const kb_batch_t *b) { return b ? b->L.n_asm : 0; }
@@ -438,6 +490,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         CU(cudaSetDevice(ix->device));
         CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         P.st = st;
+        P.arena = arena_acquire(ix->device);
         for (auto &e : ev) CU(cudaEventCreate(&e));
         const KbBatchView &bv = bt->view;
         const KbIndexView &iv = ix->view;
@@ -711,6 +764,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         CU(cudaEventElapsedTime(&R->stage_ms[KB_STAGE_TOTAL], ev[0], ev[5]));
         P.clear();
         CU(cudaStreamSynchronize(st));
+        arena_release(P.arena), P.arena = nullptr;
         for (auto &e : ev) cudaEventDestroy(e);
         cudaStreamDestroy(st);
     } catch (const std::string &e) {
@@ -719,6 +773,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             cudaStreamSynchronize(st);
             cudaStreamDestroy(st);
         }
+        arena_release(P.arena), P.arena = nullptr;
         for (auto &e2 : ev)
             if (e2) cudaEventDestroy(e2);
         kb_result_destroy(R);
@@ -808,23 +863,89 @@ int kb_result_fetch_chains(const kb_result_t *r, int32_t *out, int64_t cap, int6
     return KB_OK;
 }
 
+static int map_assemblies_once(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
+                               const int32_t *asm_contig_start, int32_t n_asm, kb_result_t **out)
+{
+    kb_batch_t *b = nullptr;
+    int rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
+    if (rc) return rc;
+    rc = kb_map_batch(ix, b, out);
+    kb_batch_destroy(b);
+    return rc;
+}
+
+// Host buffers in, host arrays out.  Inputs beyond one slab (1024 assemblies unless KAPTIVE_B200_SLAB says otherwise)
+// are cut into slabs that two host threads push through batch_create -> map on their own streams, which bounds the
+// device memory of a call and lets the H2D copy and packing of one slab overlap the kernels of the other; the slabs'
+// hits are then fetched in assembly order.  Slabs must stay large: measured on B200, 32-64 assembly slabs lose more
+// to half-empty persistent kernels than the overlap wins (scripts/e2e_probe.py).  Results do not depend on the slab
+// size (assemblies are independent units; tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
 int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
                       const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
                       int64_t cigar_cap, int64_t *n_cigar)
 {
     if (!ix) return fail(KB_ERR_ARG, "null index");
-    kb_batch_t *b = nullptr;
-    int rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
-    if (rc) return rc;
-    kb_result_t *r = nullptr;
-    rc = kb_map_batch(ix, b, &r);
-    if (rc == KB_OK) {
-        if (n_hits) *n_hits = r->n_hits;
-        if (n_cigar) *n_cigar = r->n_cigar;
-        if (dst) rc = kb_result_fetch(r, dst, cigar, cigar_cap);
-        kb_result_destroy(r);
+    if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
+    int slab = 1024;
+    if (const char *e = getenv("KAPTIVE_B200_SLAB")) slab = atoi(e) > 0 ? atoi(e) : slab;
+    const int n_slabs = n_asm <= slab + slab / 2 ? 1 : (n_asm + slab - 1) / slab;
+    std::vector<kb_result_t *> res((size_t)n_slabs, nullptr);
+    std::vector<int> rcs((size_t)n_slabs, KB_OK);
+    std::vector<std::string> errs((size_t)n_slabs);
+    auto run_slab = [&](int k) {
+        const int a0 = n_slabs == 1 ? 0 : k * slab, a1 = n_slabs == 1 ? n_asm : std::min(n_asm, a0 + slab);
+        const int c0 = asm_contig_start[a0];
+        std::vector<int32_t> acs((size_t)(a1 - a0) + 1);
+        for (int a = a0; a <= a1; ++a) acs[(size_t)(a - a0)] = asm_contig_start[a] - c0;
+        rcs[(size_t)k] = map_assemblies_once(ix, contig_seqs, contig_off + c0, contig_len + c0, acs.data(), a1 - a0, &res[(size_t)k]);
+        if (rcs[(size_t)k]) errs[(size_t)k] = g_err;  // g_err is thread local
+    };
+    if (n_slabs == 1) run_slab(0);
+    else {
+        std::atomic<int> next{0};
+        auto worker = [&]() {
+            for (int k; (k = next.fetch_add(1)) < n_slabs;) run_slab(k);
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < std::min(2, n_slabs); ++t) th.emplace_back(worker);
+        for (auto &t : th) t.join();
     }
-    kb_batch_destroy(b);
+    int rc = KB_OK;
+    int64_t tot_h = 0, tot_c = 0;
+    for (int k = 0; k < n_slabs; ++k) {
+        if (rcs[(size_t)k] && !rc) rc = fail(rcs[(size_t)k], errs[(size_t)k]);
+        if (res[(size_t)k]) tot_h += res[(size_t)k]->n_hits, tot_c += res[(size_t)k]->n_cigar;
+    }
+    if (!rc) {
+        if (n_hits) *n_hits = tot_h;
+        if (n_cigar) *n_cigar = tot_c;
+        if (dst) {
+            if (dst->capacity < tot_h) rc = fail(KB_ERR_CAPACITY, "hit arrays smaller than kb_result_size()");
+            else if (cigar && cigar_cap < tot_c) rc = fail(KB_ERR_CAPACITY, "cigar buffer smaller than kb_result_size()");
+        }
+    }
+    if (!rc && dst) {
+        int64_t oh = 0, oc = 0;
+        for (int k = 0; k < n_slabs && !rc; ++k) {
+            const kb_result_t *r = res[(size_t)k];
+            kb_hits_t v = *dst;  // a view of the caller's arrays starting at hit `oh`
+            v.capacity = dst->capacity - oh;
+#define OFF(f) \
+    if (v.f) v.f += oh
+            OFF(asm_id); OFF(gene); OFF(q_start); OFF(q_end); OFF(t_ctg); OFF(t_len); OFF(t_start); OFF(t_end); OFF(strand); OFF(score);
+            OFF(matches); OFF(block_len); OFF(edit_distance); OFF(mapq); OFF(is_primary); OFF(cigar_off); OFF(n_cigar);
+#undef OFF
+            rc = kb_result_fetch(r, &v, cigar ? cigar + oc : nullptr, cigar_cap - oc);
+            const int a0 = n_slabs == 1 ? 0 : k * slab;
+            if (!rc && (a0 || oc))
+                for (int64_t i = 0; i < r->n_hits; ++i) {
+                    if (v.asm_id) v.asm_id[i] += a0;
+                    if (v.cigar_off) v.cigar_off[i] += oc;
+                }
+            oh += r->n_hits, oc += r->n_cigar;
+        }
+    }
+    for (kb_result_t *r : res) kb_result_destroy(r);
     return rc;
 }
 

@@ -221,3 +221,39 @@ def test_divergence_ladder_equals_oracle(env):
         check_against(res, ai, ro["hits"], ro["cigar"])
         total += len(ro["hits"])
     assert total > 200
+
+
+def test_host_buffer_entry_point_slabs_equal_batch_path(env, monkeypatch):
+    """kb_map_assemblies cuts large inputs into slabs that overlap copies and kernels; hits must come back in assembly
+    order with the same values as one batch (slab size forced down to 2 assemblies so that 7 assemblies make 4 slabs)."""
+    from kaptive_b200 import _lib
+
+    monkeypatch.setenv("KAPTIVE_B200_SLAB", "2")
+    names = env["names"][:7]
+    seqs, off, ln, acs = [], [], [], [0]
+    base = 0
+    for n in names:
+        s, o, l = cases.flat_contigs(env["built"][n][1])
+        seqs.append(s), off.append(o + base), ln.append(l)
+        base += len(s)
+        acs.append(acs[-1] + len(l))
+    seqs, off, ln = np.concatenate(seqs), np.concatenate(off).astype(np.int64), np.concatenate(ln).astype(np.int32)
+    acs = np.array(acs, dtype=np.int32)
+    h, arrays = env["mapper"].alloc_hits(1 << 14)
+    cig = np.zeros(1 << 18, dtype=np.uint32)
+    nh, nc = C.c_int64(0), C.c_int64(0)
+    L = _lib.load()
+    _lib.check(L.kb_map_assemblies(env["gi"]._h, _lib.ptr(seqs), _lib.ptr(off), _lib.ptr(ln), _lib.ptr(acs), len(names), C.byref(h),
+                                   C.byref(nh), _lib.ptr(cig), len(cig), C.byref(nc)))
+    k = 0
+    for ai, n in enumerate(names):
+        g, gc = GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"]
+        sel = slice(k, k + len(g))
+        assert np.all(arrays["asm_id"][sel] == ai)
+        for f in FIELDS:
+            assert np.array_equal(arrays[f][sel].astype(np.int64), g[f].astype(np.int64)), (n, f)
+        for j in range(len(g)):
+            co, ncg = int(arrays["cigar_off"][k + j]), int(arrays["n_cigar"][k + j])
+            assert np.array_equal(cig[co : co + ncg], gc[g["cigar_off"][j] : g["cigar_off"][j] + g["n_cigar"][j]])
+        k += len(g)
+    assert k == nh.value
