@@ -348,6 +348,7 @@ static __device__ __noinline__ int kb_global_bandK(const KbDpConst P, int lane, 
 {
     int dlo, dhi;
     const int r_end = tlen + qlen;
+    ez.score = KB_NEG_INF;
     if (!kb_band_geometry(qlen, tlen, K, dlo, dhi) || (int64_t)32 * K * (r_end + 8) > P.max_sw_cells) return 0;
     const KbC8 c = kb_c8(P, 0);
     uint8_t *tb = S.tb;  // [r'][lane][K]
@@ -437,7 +438,10 @@ static __device__ __noinline__ int kb_global_bandK(const KbDpConst P, int lane, 
     for (int m = 1; m < K; ++m)
         if (m == cend % K) hv = H1[m];
     const int score = __shfl_sync(0xffffffffu, hv, (cend / K) & 31) >> 3;
-    if (!(score > kb_band_bound(P, qlen, tlen, dlo, dhi))) return 0;
+    if (!(score > kb_band_bound(P, qlen, tlen, dlo, dhi))) {
+        ez.score = score;  // still a valid alignment's score: a lower bound for any wider band
+        return 0;
+    }
     __syncwarp();
     int bad = 0;
     const int n_cigar = kb_backtrack_warp(lane, tlen - 1, qlen - 1, 0, flag, S.ezcig, [&](int i, int j) -> uint32_t {

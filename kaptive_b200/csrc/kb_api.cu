@@ -641,7 +641,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         int64_t n_raw = 0, n_pool = 0;
         uint32_t *pool = nullptr;
         size_t sbytes = kb_align_scratch_bytes(p.max_sw_cells);
-        int n_warps = bt->n_sm * 16;
+        int n_warps = bt->n_sm * 24;  // resident warps of the DP kernels (6 CTAs of 4 warps per SM)
         {
             int64_t need_warps = ((n_chains + 3) / 4) * 4;
             if (need_warps < 4) need_warps = 4;
@@ -653,7 +653,9 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         const char *sg = getenv("KAPTIVE_B200_STAGED");
         const bool staged = !(sg && sg[0] == '0') && n_chains > 0;
         const int64_t job_cap = n_chains * 12 + 4096, jobcig_cap = job_cap * 16;
-        const int band_warps = bt->n_sm * 16, rows_warps = n_warps;
+        int band_warps = bt->n_sm * 24, rows_warps = n_warps;
+        if (const char *e = getenv("KAPTIVE_B200_BAND_WARPS")) band_warps = bt->n_sm * atoi(e);
+        if (const char *e = getenv("KAPTIVE_B200_ROWS_WARPS")) rows_warps = std::min(n_warps, bt->n_sm * atoi(e));
         void *plans = nullptr, *jobs = nullptr;
         int32_t *band_list = nullptr, *rows_list = nullptr, *slow_list = nullptr, *kscratch = nullptr;
         uint32_t *jobcig = nullptr, *tmpcig = nullptr;

@@ -320,7 +320,10 @@ static __device__ __forceinline__ void kb_job_finish(int lane, KbJob *J, const K
 }
 
 // certified band pass over the gap fills: one warp per job, persistent, dynamic queue
-__global__ void __launch_bounds__(128, 4) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, int32_t *rows_list,
+#ifndef KB_BAND_MINB
+#define KB_BAND_MINB 6
+#endif
+__global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, int32_t *rows_list,
                                                         uint8_t *scratch, size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
                                                         unsigned long long *counters)
 {
@@ -363,7 +366,10 @@ __global__ void __launch_bounds__(128, 4) kb_band_kernel(KbIndexView ix, KbBatch
 }
 
 // row-stripe wavefront over everything else (end extensions, fills the band pass could not certify)
-__global__ void __launch_bounds__(128, 4) kb_rows_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *rows_list, uint8_t *scratch,
+#ifndef KB_ROWS_MINB
+#define KB_ROWS_MINB 6  // 80 registers, 24 warps per SM: measured 8 % faster than 128 registers / 16 warps (profiles/r1_summary.md)
+#endif
+__global__ void __launch_bounds__(128, KB_ROWS_MINB) kb_rows_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *rows_list, uint8_t *scratch,
                                                         size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
                                                         unsigned long long *counters)
 {
