@@ -314,9 +314,22 @@ def run_ours(a):
     scan_ms = stage_acc.get("scan", 0.0) / a.steps
     alg_bytes = packed_bytes + 12 * counters.get("anchors", 0)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    traffic = None  # dram read + write bytes of one scan launch from the committed ncu --set full capture of this workload
+    try:
+        t = json.loads((ROOT / "profiles" / "scan_traffic.json").read_text())
+        if int(t["assemblies_per_launch"]) == a.n_asm and int(t["asm_len"]) == a.asm_len:
+            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "kb_scan_kernel<10,15>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": scan_ms}
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": scan_ms,
+                "note": "the sketch is integer-issue bound (about 170 instructions per 32 bases): see DESIGN.md section 4"}
+    align_ms = stage_acc.get("align", 0.0) / a.steps
+    dominant = {"kernels": "kb_rows_kernel + kb_band_kernel (base-level DP)", "share_of_step": align_ms / dev_ms if dev_ms else None,
+                "dp_cells_per_step": int(counters.get("dp_cells", 0)),
+                "gcups": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 if align_ms else None,
+                "bound": "integer issue (ALU pipe), not HBM: 1 B of traceback per cell"}
 
     cpu = None
     if not a.no_cpu_baseline:
@@ -343,6 +356,7 @@ def run_ours(a):
         "gpu_launches": int(counters.get("launches", 0)) * a.steps,
         "clocks": clocks,
         "roofline": roofline,
+        "dominant": dominant,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
