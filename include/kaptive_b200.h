@@ -168,6 +168,16 @@ int kb_post_translate(const uint8_t *seqs, int64_t n_seq_bytes, const int64_t *o
 int kb_post_protein_align(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t, const int64_t *t_off,
                           const int32_t *t_len, int32_t n, int32_t k, int32_t gap_open, int32_t gap_extend, int32_t *res);
 
+/* _cull_overlaps_kernel (src/kaptive/core/interval.py:698-751; driven by Alignments.cull_overlaps, core/alignment.py:643-686):
+ * greedy overlap cull in the given evaluation order, batched over segments (one segment = the hits of one assembly).  Arrays are
+ * concatenated over the segments, seg_off has n_seg + 1 entries, `order` holds indices local to each segment.  kept: 0 / 1 per hit. */
+int kb_post_cull_overlaps(const int32_t *order, const int32_t *group1, const int32_t *group2, const int32_t *starts, const int32_t *ends,
+                          double max_overlap_fraction, const int64_t *seg_off, int32_t n_seg, uint8_t *kept);
+/* _cluster_kernel (src/kaptive/core/interval.py:595-639; driven by Intervals.cluster_spatial :471-493): single-linkage clustering
+ * of intervals swept in `order`; cluster ids restart at 0 in every segment. */
+int kb_post_cluster(const int32_t *starts, const int32_t *ends, const int32_t *groups, int32_t tolerance, const int32_t *order,
+                    const int64_t *seg_off, int32_t n_seg, int32_t *cluster_ids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ _SYMBOLS = [
     ("kb_post_extract", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int64, _P, _P]),
     ("kb_post_translate", C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]),
     ("kb_post_protein_align", C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    ("kb_post_cull_overlaps", C.c_int, [_P, _P, _P, _P, _P, C.c_double, _P, C.c_int32, _P]),
+    ("kb_post_cluster", C.c_int, [_P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
 ]  # fmt: skip
 
 _lib = None

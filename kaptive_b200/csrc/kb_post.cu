@@ -3,6 +3,8 @@
 //   kb_post_extract        replaces _extract_ragged_kernel   (src/kaptive/core/seq.py:612-668; called serotyping/core.py:333,352)
 //   kb_post_translate      replaces _translate_ragged_kernel (src/kaptive/core/seq.py:671-741; called serotyping/core.py:360)
 //   kb_post_protein_align  replaces _batched_banded_gotoh    (src/kaptive/core/pairwise.py:395-584; called serotyping/core.py:378)
+//   kb_post_cull_overlaps  replaces _cull_overlaps_kernel    (src/kaptive/core/interval.py:698-751; via Alignments.cull_overlaps)
+//   kb_post_cluster        replaces _cluster_kernel          (src/kaptive/core/interval.py:595-639; via Intervals.cluster_spatial)
 //
 // The reference launches each of these once per assembly on ~20-60 items, which costs it ~6 ms of numba parallel-region
 // wake-up per call; here one call handles the items of a whole batch of assemblies.  Bit-exact: integer/byte work only.
@@ -10,6 +12,7 @@
 // live rows and a 1-byte/cell packed traceback in global scratch -- thousands of independent pairs per call are the
 // parallelism, exactly as in the reference's prange.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "kb_common.cuh"
@@ -228,6 +231,61 @@ __global__ void gotoh_kernel(const uint8_t *q, const int64_t *q_off, const int32
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row a8: greedy overlap cull (one warp per segment: the hit under test is compared with the kept list 32 entries at a
+// time) and 1-D single-linkage clustering (one thread per segment, a sequential sweep in the given order).
+__global__ void kb_cull_kernel(const int32_t *order, const int32_t *g1, const int32_t *g2, const int32_t *starts, const int32_t *ends,
+                               double frac, const int64_t *seg_off, int32_t n_seg, int32_t *kept_list, uint8_t *kept)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp; s < n_seg; s += n_warps) {
+        const int64_t b = seg_off[s];
+        const int32_t n = (int32_t)(seg_off[s + 1] - b);
+        int32_t *kl = kept_list + b;  // global indices of the kept hits, in evaluation order
+        int32_t nk = 0;
+        for (int32_t i = lane; i < n; i += 32) kept[b + i] = 0;
+        __syncwarp();
+        for (int32_t i = 0; i < n; ++i) {
+            const int64_t idx = b + order[b + i];
+            const int32_t a1 = g1[idx], a2 = g2[idx], st = starts[idx], en = ends[idx], length = en - st;
+            if (length <= 0) continue;  // warp-uniform
+            bool found = false;
+            for (int32_t j = lane; j < nk; j += 32) {
+                const int64_t p = kl[j];
+                if (g1[p] != a1 || g2[p] != a2) continue;
+                const int32_t ks = starts[p], ke = ends[p];
+                const int32_t ov = min(en, ke) - max(st, ks), mn = min(length, ke - ks);
+                if (ov > 0 && ((double)ov / (double)mn) > frac) found = true;
+            }
+            if (!__any_sync(0xffffffffu, found)) {
+                if (lane == 0) kept[idx] = 1, kl[nk] = (int32_t)idx;
+                ++nk;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+__global__ void kb_cluster_kernel(const int32_t *starts, const int32_t *ends, const int32_t *groups, int32_t tolerance, const int32_t *order,
+                                  const int64_t *seg_off, int32_t n_seg, int32_t *cluster_ids)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const int64_t b = seg_off[s];
+    const int32_t n = (int32_t)(seg_off[s + 1] - b);
+    if (n == 0) return;
+    int32_t cur = 0, cur_e = ends[b + order[b]], cur_g = groups[b + order[b]];
+    cluster_ids[b + order[b]] = 0;
+    for (int32_t i = 1; i < n; ++i) {
+        const int64_t idx = b + order[b + i];
+        const int32_t st = starts[idx], en = ends[idx], g = groups[idx];
+        if (g == cur_g && st <= cur_e + tolerance) cur_e = max(cur_e, en);
+        else ++cur, cur_e = en, cur_g = g;
+        cluster_ids[idx] = cur;
+    }
+}
+
 extern "C" {
 
 const char *kb_post_last_error(void) { return g_post_err.c_str(); }
@@ -337,6 +395,60 @@ int kb_post_protein_align(const uint8_t *q, const int64_t *q_off, const int32_t 
         gotoh_kernel<<<(n + 63) / 64, 64>>>(d_q, d_qo, d_ql, d_t, d_to, d_tl, n, k, gap_open, gap_extend, d_tbo, d_tb, d_ro, d_rows, d_res);
         PCU(cudaGetLastError());
         PCU(cudaMemcpy(res, d_res, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+/* _cull_overlaps_kernel (src/kaptive/core/interval.py:698-751), one call for the hits of many assemblies. */
+int kb_post_cull_overlaps(const int32_t *order, const int32_t *group1, const int32_t *group2, const int32_t *starts, const int32_t *ends,
+                          double max_overlap_fraction, const int64_t *seg_off, int32_t n_seg, uint8_t *kept)
+{
+    if (n_seg < 0 || !seg_off || (n_seg > 0 && (!order || !group1 || !group2 || !starts || !ends || !kept))) {
+        g_post_err = "null argument";
+        return KB_ERR_ARG;
+    }
+    try {
+        ensure_device();
+        const int64_t n = n_seg ? seg_off[n_seg] : 0;
+        if (n == 0) return KB_OK;
+        Dev D;
+        const int32_t *d_order = D.upload(order, (size_t)n), *d_g1 = D.upload(group1, (size_t)n), *d_g2 = D.upload(group2, (size_t)n);
+        const int32_t *d_st = D.upload(starts, (size_t)n), *d_en = D.upload(ends, (size_t)n);
+        const int64_t *d_off = D.upload(seg_off, (size_t)n_seg + 1);
+        int32_t *d_kl = D.alloc<int32_t>((size_t)n);
+        uint8_t *d_kept = D.alloc<uint8_t>((size_t)n);
+        const int64_t blocks = std::min<int64_t>(((int64_t)n_seg + 3) / 4, 148 * 16);
+        kb_cull_kernel<<<(unsigned)blocks, 128>>>(d_order, d_g1, d_g2, d_st, d_en, max_overlap_fraction, d_off, n_seg, d_kl, d_kept);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost));
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+/* _cluster_kernel (src/kaptive/core/interval.py:595-639), one call for the hits of many assemblies; ids restart at 0 per segment. */
+int kb_post_cluster(const int32_t *starts, const int32_t *ends, const int32_t *groups, int32_t tolerance, const int32_t *order,
+                    const int64_t *seg_off, int32_t n_seg, int32_t *cluster_ids)
+{
+    if (n_seg < 0 || !seg_off || (n_seg > 0 && (!order || !groups || !starts || !ends || !cluster_ids))) {
+        g_post_err = "null argument";
+        return KB_ERR_ARG;
+    }
+    try {
+        ensure_device();
+        const int64_t n = n_seg ? seg_off[n_seg] : 0;
+        if (n == 0) return KB_OK;
+        Dev D;
+        const int32_t *d_st = D.upload(starts, (size_t)n), *d_en = D.upload(ends, (size_t)n), *d_g = D.upload(groups, (size_t)n);
+        const int32_t *d_order = D.upload(order, (size_t)n);
+        const int64_t *d_off = D.upload(seg_off, (size_t)n_seg + 1);
+        int32_t *d_ids = D.alloc<int32_t>((size_t)n);
+        kb_cluster_kernel<<<(unsigned)((n_seg + 127) / 128), 128>>>(d_st, d_en, d_g, tolerance, d_order, d_off, n_seg, d_ids);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpy(cluster_ids, d_ids, (size_t)n * 4, cudaMemcpyDeviceToHost));
     } catch (const std::string &) {
         return KB_ERR_CUDA;
     }

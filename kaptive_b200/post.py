@@ -1,5 +1,6 @@
 """Post-mapping numerics on the GPU: batched replacements of the reference's numba kernels
-(``core/seq.py:612-668`` extract, ``core/seq.py:671-741`` translate, ``core/pairwise.py:395-584`` protein Gotoh).
+(``core/seq.py:612-668`` extract, ``core/seq.py:671-741`` translate, ``core/pairwise.py:395-584`` protein Gotoh,
+``core/interval.py:698-751`` overlap cull, ``core/interval.py:595-639`` spatial clustering).
 Arrays in, one C-ABI call, arrays out; no CPU fallback."""
 
 from __future__ import annotations
@@ -68,3 +69,41 @@ def protein_align(q, q_len, t, t_len, k: int = 20, gap_open: int = 11, gap_exten
     _check(L.kb_post_protein_align(ptr(q), ptr(_offsets(q_len)), ptr(q_len), ptr(t), ptr(_offsets(t_len)), ptr(t_len), n, k, gap_open, gap_extend,
                                    ptr(res)))
     return res[:n]
+
+
+def _local_order(keys: tuple, seg_off: np.ndarray) -> np.ndarray:
+    """np.lexsort within every segment (the reference sorts one assembly at a time); indices local to the segment."""
+    order = np.zeros(int(seg_off[-1]), np.int32)
+    for s in range(len(seg_off) - 1):
+        a, b = int(seg_off[s]), int(seg_off[s + 1])
+        if b > a:
+            order[a:b] = np.lexsort(tuple(k[a:b] for k in keys)).astype(np.int32)
+    return order
+
+
+def cull_overlaps(starts, ends, group1, group2, scores, matches, mapq, seg_off, max_overlap_fraction: float = 0.1,
+                  priority_mask=None) -> np.ndarray:
+    """``Alignments.cull_overlaps`` (reference core/alignment.py:643-686) for the hits of many assemblies at once: evaluation order
+    = score (+1e9 where ``priority_mask``), then matches, then mapq, all descending (:669-675); returns the boolean kept mask."""
+    L = _lib.load()
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    sc = np.asarray(scores, np.float64).copy()
+    if priority_mask is not None:
+        sc[np.asarray(priority_mask, bool)] += 1e9
+    order = _local_order((-np.asarray(mapq).astype(np.int32), -np.asarray(matches).astype(np.int64), -sc), seg_off)
+    a = [np.ascontiguousarray(x, np.int32) for x in (group1, group2, starts, ends)]
+    kept = np.zeros(max(int(seg_off[-1]), 1), np.uint8)
+    _check(L.kb_post_cull_overlaps(ptr(order), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), float(max_overlap_fraction), ptr(seg_off),
+                                   len(seg_off) - 1, ptr(kept)))
+    return kept[: int(seg_off[-1])].astype(bool)
+
+
+def cluster_spatial(starts, ends, groups, seg_off, tolerance: int = 0) -> np.ndarray:
+    """``Intervals.cluster_spatial`` (reference core/interval.py:471-493) per segment: order = lexsort((ends, starts, groups))."""
+    L = _lib.load()
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    st, en, g = (np.ascontiguousarray(x, np.int32) for x in (starts, ends, groups))
+    order = _local_order((en, st, g), seg_off)
+    ids = np.zeros(max(int(seg_off[-1]), 1), np.int32)
+    _check(L.kb_post_cluster(ptr(st), ptr(en), ptr(g), int(tolerance), ptr(order), ptr(seg_off), len(seg_off) - 1, ptr(ids)))
+    return ids[: int(seg_off[-1])]

@@ -17,6 +17,8 @@ def _lib():
         L.kbo_translate.restype = C.c_int64
         L.kbo_translate.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + [C.c_void_p] * 3
         L.kbo_protein_align.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_void_p]
+        L.kbo_cull_overlaps.argtypes = [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_int32, C.c_void_p]
+        L.kbo_cluster.argtypes = [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L._post_bound = True
     return L
 
@@ -54,3 +56,20 @@ def protein_align(q, q_len, t, t_len, k=20, gap_open=11, gap_extend=1):
          np.ascontiguousarray(t, np.uint8), offsets_of(t_len), np.ascontiguousarray(t_len, np.int32)]
     _lib().kbo_protein_align(*[_ptr(x) for x in a], n, k, gap_open, gap_extend, _ptr(res))
     return res
+
+
+def cull_overlaps(order, g1, g2, starts, ends, frac, seg_off):
+    a = [np.ascontiguousarray(x, np.int32) for x in (order, g1, g2, starts, ends)]
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    kept = np.zeros(max(int(seg_off[-1]), 1), np.uint8)
+    _lib().kbo_cull_overlaps(*[_ptr(x) for x in a], float(frac), _ptr(seg_off), len(seg_off) - 1, _ptr(kept))
+    return kept[: int(seg_off[-1])]
+
+
+def cluster(starts, ends, groups, tol, order, seg_off):
+    a = [np.ascontiguousarray(x, np.int32) for x in (starts, ends, groups)]
+    order = np.ascontiguousarray(order, np.int32)
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    ids = np.zeros(max(int(seg_off[-1]), 1), np.int32)
+    _lib().kbo_cluster(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), int(tol), _ptr(order), _ptr(seg_off), len(seg_off) - 1, _ptr(ids))
+    return ids[: int(seg_off[-1])]

@@ -1,4 +1,4 @@
-"""Post-mapping stages (SURVEY.md section 8 rows a6/a7): the oracle restatement against vectors produced by the
+"""Post-mapping stages (SURVEY.md section 8 rows a6/a7/a8): the oracle restatement against vectors produced by the
 reference's own numba kernels (tests/golden/post_golden.npz), and -- on the GPU tier -- the CUDA kernels against both."""
 
 from pathlib import Path
@@ -73,3 +73,59 @@ def test_gpu_post_kernels_match_golden_and_oracle():
     ql, tl = np.array([len(x) for x in qs], np.int32), np.array([len(x) for x in ts], np.int32)
     Q, T = np.concatenate(qs), np.concatenate(ts)
     assert np.array_equal(post.protein_align(Q, ql, T, tl), po.protein_align(Q, ql, T, tl))
+
+
+# ---------------------------------------------------------------------------------------------- row a8: cull + cluster
+A8 = np.load(Path(__file__).resolve().parent / "golden" / "a8_golden.npz")
+
+
+def _a8_segments():
+    off = A8["seg_off"]
+    for s in range(len(off) - 1):
+        yield s, slice(int(off[s]), int(off[s + 1]))
+
+
+def test_oracle_cull_and_cluster_match_reference_kernels():
+    """oracle/kb_post_oracle.c vs vectors of the reference's _cull_overlaps_kernel / _cluster_kernel (make_golden_a8.py);
+    max_overlap_fraction and tolerance differ per segment, so the oracle is called one segment at a time."""
+    for s, sl in _a8_segments():
+        so = np.array([0, sl.stop - sl.start], np.int64)
+        kept = po.cull_overlaps(A8["order_cull"][sl], A8["g1"][sl], A8["g2"][sl], A8["st"][sl], A8["en"][sl], A8["frac"][s], so)
+        assert np.array_equal(kept, A8["kept"][sl]), s
+        ids = po.cluster(A8["st"][sl], A8["en"][sl], A8["g1"][sl], A8["tol"][s], A8["order_cl"][sl], so)
+        assert np.array_equal(ids, A8["cl"][sl]), s
+
+
+def test_oracle_cull_batched_equals_per_segment():
+    same = np.nonzero(A8["frac"] == 0.1)[0]
+    off = A8["seg_off"]
+    parts = [slice(int(off[s]), int(off[s + 1])) for s in same]
+    cat = lambda k: np.concatenate([A8[k][p] for p in parts])  # noqa: E731
+    so = np.concatenate([[0], np.cumsum([p.stop - p.start for p in parts])]).astype(np.int64)
+    kept = po.cull_overlaps(cat("order_cull"), cat("g1"), cat("g2"), cat("st"), cat("en"), 0.1, so)
+    assert np.array_equal(kept, cat("kept"))
+
+
+@pytest.mark.gpu
+def test_gpu_cull_and_cluster_match_reference_kernels():
+    """CUDA kernels through kaptive_b200.post (which also derives the evaluation order the way the reference does) against
+    the reference's own outputs, batched over all segments that share a parameter value."""
+    from kaptive_b200 import post
+
+    off = A8["seg_off"]
+    for frac in np.unique(A8["frac"]):
+        segs = np.nonzero(A8["frac"] == frac)[0]
+        parts = [slice(int(off[s]), int(off[s + 1])) for s in segs]
+        cat = lambda k: np.concatenate([A8[k][p] for p in parts])  # noqa: E731
+        so = np.concatenate([[0], np.cumsum([p.stop - p.start for p in parts])]).astype(np.int64)
+        kept = post.cull_overlaps(cat("st"), cat("en"), cat("g1"), cat("g2"), cat("score"), cat("matches"), cat("mapq"), so, float(frac))
+        assert np.array_equal(kept, cat("kept").astype(bool))
+    for tol in np.unique(A8["tol"]):
+        segs = np.nonzero(A8["tol"] == tol)[0]
+        parts = [slice(int(off[s]), int(off[s + 1])) for s in segs]
+        cat = lambda k: np.concatenate([A8[k][p] for p in parts])  # noqa: E731
+        so = np.concatenate([[0], np.cumsum([p.stop - p.start for p in parts])]).astype(np.int64)
+        ids = post.cluster_spatial(cat("st"), cat("en"), cat("g1"), so, int(tol))
+        assert np.array_equal(ids, cat("cl"))
+    # empty batch
+    assert len(post.cull_overlaps([], [], [], [], [], [], [], [0], 0.1)) == 0
