@@ -655,6 +655,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         const int64_t job_cap = n_chains * 12 + 4096, jobcig_cap = job_cap * 16;
         int band_warps = bt->n_sm * 24, rows_warps = n_warps;
         if (const char *e = getenv("KAPTIVE_B200_BAND_WARPS")) band_warps = bt->n_sm * atoi(e);
+        if ((int64_t)band_warps > 4 * n_chains + 4) band_warps = (int)(((4 * n_chains + 4) + 3) / 4 * 4);  // small calls: small scratch
         if (const char *e = getenv("KAPTIVE_B200_ROWS_WARPS")) rows_warps = std::min(n_warps, bt->n_sm * atoi(e));
         void *plans = nullptr, *jobs = nullptr;
         int32_t *band_list = nullptr, *rows_list = nullptr, *slow_list = nullptr, *kscratch = nullptr;

@@ -257,3 +257,38 @@ def test_host_buffer_entry_point_slabs_equal_batch_path(env, monkeypatch):
             assert np.array_equal(cig[co : co + ncg], gc[g["cigar_off"][j] : g["cigar_off"][j] + g["n_cigar"][j]])
         k += len(g)
     assert k == nh.value
+
+
+def test_combined_k_and_o_database_and_fragmentation_ladder_equal_oracle(env):
+    """BASELINE.json configs[2] and configs[4] as parity cases: a combined K+O-shaped gene set (150 x 20 genes would be
+    the bench size; here 14 x 10 K genes + 5 x 6 O genes + 4 extra genes in ONE index), assemblies carrying both a K and an O
+    locus, and a depth-like fragmentation ladder (mean contig count 3 -> 400 on a 300 kb genome, i.e. contig N50 from
+    ~100 kb down to < 1 kb, the locus broken into 1-8+ pieces).  Every hit equals the oracle's, so any call the unmodified
+    typing logic derives from the hits (best locus, typeable) is concordant by construction."""
+    from kaptive_b200 import synth
+
+    k = synth.make_db(n_loci=14, genes_per_locus=10, n_core=3, seed=21, prefix="KL")
+    o = synth.make_db(n_loci=5, genes_per_locus=6, n_core=2, n_extra=4, seed=22, prefix="OL")
+    genes = k.genes + o.genes
+    loci = k.loci + o.loci
+    db = synth.SynthDB(genes=genes, gene_locus=np.concatenate([k.gene_locus, o.gene_locus + len(k.loci)]),
+                       gene_pos=np.concatenate([k.gene_pos, o.gene_pos]), gene_start=np.concatenate([k.gene_start, o.gene_start]),
+                       gene_end=np.concatenate([k.gene_end, o.gene_end]), gene_strand=np.concatenate([k.gene_strand, o.gene_strand]),
+                       extra=np.concatenate([k.extra, o.extra]), loci=loci, locus_names=k.locus_names + o.locus_names)
+    gi = env["mapper"].GeneIndex(db.genes)
+    asms = []
+    ladder = [3, 6, 12, 25, 50, 100, 200, 400]
+    for i, mc in enumerate(ladder * 2):
+        kl, ol_ = i % 14, 14 + i % 5
+        asms.append(synth.make_assembly(db, kl, seed=8100 + i, genome_len=300_000, mean_contigs=mc, extra_loci=(ol_,),
+                                        sub=(0.0, 0.04), indel=(0.0, 0.004)))
+    res = gi.map_contigs([[s for _, s in a.contigs] for a in asms])
+    odb = ol.OracleDB(*db.flat())
+    n_k = n_o = 0
+    for ai, a in enumerate(asms):
+        ro = odb.map(*a.flat())
+        check_against(res, ai, ro["hits"], ro["cigar"])
+        g = ro["hits"]["gene"]
+        n_k += int((g < len(k.genes)).sum())
+        n_o += int((g >= len(k.genes)).sum())
+    assert n_k > 100 and n_o > 40
