@@ -157,7 +157,7 @@ def run_reference(a):
 
     cores = os.cpu_count() or 1
     db = synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1)
-    n = a.cpu_sample or max(2, min(2 * cores, 16))
+    n = a.cpu_sample or max(2, min(4 * cores, 96))
     sample = host_sample(a, db, n)
     for _ in range(min(a.warmup, 1)):
         cpu_oracle_rate(db, sample[: max(1, min(cores, n))], cores)
@@ -334,7 +334,7 @@ def run_ours(a):
     cpu = None
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = a.cpu_sample or max(2, min(2 * cores, 16))
+        n = a.cpu_sample or max(2, min(4 * cores, 96))  # about 10 s of CPU work on the box's cores
         sample = host_sample(a, db, n)
         rate, secs = cpu_oracle_rate(db, sample, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

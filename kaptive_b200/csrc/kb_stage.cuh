@@ -54,10 +54,19 @@ struct KbByteSeq {
     KB_HD int operator[](int x) const { return p[x]; }
     KB_HD KbByteSeq operator+(int d) const { return KbByteSeq{p + d}; }
 };
-struct KbPackSeq {
+struct KbPackSeq {  // remembers the last 32-base group it touched: the assembly code reads bases in sequence
     const uint32_t *seq2, *nmask;
     int64_t pos;
-    KB_HD int operator[](int x) const { return kb_fetch_base(seq2, nmask, pos + x); }
+    mutable int64_t grp = -1;
+    mutable uint32_t w0 = 0, w1 = 0, mw = 0;
+    KB_HD int operator[](int x) const
+    {
+        const int64_t b = pos + x, g = b >> 5;
+        if (g != grp) grp = g, w0 = seq2[2 * g], w1 = seq2[2 * g + 1], mw = nmask[g];
+        const int r = (int)(b & 31);
+        if ((mw >> r) & 1u) return 4;
+        return (int)(((r < 16 ? w0 : w1) >> (2 * (r & 15))) & 3u);
+    }
     KB_HD KbPackSeq operator+(int d) const { return KbPackSeq{seq2, nmask, pos + d}; }
 };
 
