@@ -866,11 +866,16 @@ int kb_result_fetch_chains(const kb_result_t *r, int32_t *out, int64_t cap, int6
     return KB_OK;
 }
 
+static std::mutex g_h2d_mu;  // one slab copies at a time: two concurrent H2D streams only halve each other's bandwidth
 static int map_assemblies_once(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
                                const int32_t *asm_contig_start, int32_t n_asm, kb_result_t **out)
 {
     kb_batch_t *b = nullptr;
-    int rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(g_h2d_mu);
+        rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
+    }
     if (rc) return rc;
     rc = kb_map_batch(ix, b, out);
     kb_batch_destroy(b);
