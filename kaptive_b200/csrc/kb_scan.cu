@@ -4,14 +4,16 @@
 // quoted on (DESIGN.md "Scan kernel").
 //
 // Work decomposition: one warp per chunk of KB_CHUNK_BASES (8192) bases of one
-// contig; lane L owns bases [L*256, (L+1)*256) of the chunk.  Each lane pulls
-// its 64 B of 2-bit sequence and 32 B of ambiguity mask with 16-byte loads
-// (a warp reads 2 KB + 1 KB contiguous), obtains the 24-base look-back from
-// its left neighbour by shuffle, and runs the sketch state machine entirely in
-// registers.  Minimizers go to a per-warp shared-memory queue; every time the
-// queue holds >= 32 the warp drains it: one hash-table probe per lane (the
-// table lives in L2), warp-aggregated allocation of anchor slots (one global
-// atomic per drain), cooperative expansion of multi-occurrence minimizers.
+// contig; lane L owns bases [L*256, (L+1)*256) of the chunk and reads them 16 at
+// a time (one 32-bit word of 2-bit sequence per 16 steps, one mask word per 32:
+// every byte of the batch is read exactly once, through L1), starts 24 bases
+// early in silent mode to rebuild the sketch state, keeps the rolling k-mers and
+// minima in registers and the w-entry window in shared memory.  An emitted
+// minimizer asks the presence bitmap (load issued one step ahead); survivors go
+// to a per-warp shared-memory queue; every time the queue holds >= 32 the warp
+// drains it: one hash-table probe per lane (the table lives in L2),
+// warp-aggregated allocation of anchor slots (one global atomic per drain),
+// cooperative expansion of multi-occurrence minimizers.
 #include "kb_scan.cuh"
 #include "kb_kernels.h"
 
@@ -46,49 +48,6 @@ KB_HD bool kb_ht_lookup(const uint64_t *ht, uint32_t ht_mask, uint32_t hash, uin
 struct ScanQueue {
     uint32_t x[KB_QCAP];
     uint32_t y[KB_QCAP];
-};
-
-// Per-lane view of the staged chunk in shared memory.  Lane L owns 18 sequence
-// words (2 look-back + 16) at stride 19 and 9 mask words (1 look-back + 8) at
-// stride 9: odd strides keep the 32 lanes on 32 different banks.
-#define KB_SEQ_STRIDE 19
-#define KB_MSK_STRIDE 9
-struct LaneFetch {
-    const uint32_t *w;  // this lane's 18 sequence words
-    const uint32_t *m;  // this lane's 9 mask words
-    int base0;          // contig position of bit 0 of w[2] (lane start, multiple of 256)
-    __device__ __forceinline__ int operator()(int i) const
-    {
-        int r = i - base0 + 32;  // >= 8 because i >= base0 - 24
-        uint32_t word = w[r >> 4];
-        uint32_t mw = m[r >> 5];
-        int c = (int)((word >> (2 * (r & 15))) & 3u);
-        return ((mw >> (r & 31)) & 1u) ? 4 : c;
-    }
-};
-
-// W sketch steps (compile-time window slots) with the ballot-based queue push between them.
-template <int W, int K, int U, class Slow>
-struct KbScanUnroll {
-    __device__ __forceinline__ static void run(KbFastSketch<W, K> &s, int i0, int i_end, int live_from, const LaneFetch &F, Slow &slow,
-                                               ScanQueue &Q, int &front, int lane)
-    {
-        const int i = i0 + U;
-        uint32_t ex = 0, ey = 0;
-        bool e = false;
-        if (i < i_end) e = kb_fast_step<W, K, U>(s, i, F(i), i >= live_from, &ex, &ey, slow);
-        const unsigned bal = __ballot_sync(0xffffffffu, e);
-        if (e) {
-            const int o = front + __popc(bal & ((1u << lane) - 1u));
-            Q.x[o] = ex, Q.y[o] = ey;
-        }
-        front += __popc(bal);
-        KbScanUnroll<W, K, U + 1, Slow>::run(s, i0, i_end, live_from, F, slow, Q, front, lane);
-    }
-};
-template <int W, int K, class Slow>
-struct KbScanUnroll<W, K, W, Slow> {
-    __device__ __forceinline__ static void run(KbFastSketch<W, K> &, int, int, int, const LaneFetch &, Slow &, ScanQueue &, int &, int) {}
 };
 
 // The sketch step of kb_fast_step (kb_scan.cuh) with the window in shared memory instead of registers: the slot is a
@@ -166,7 +125,7 @@ __device__ __forceinline__ bool kb_fast_step_sm(KbSketchRegs &s, uint32_t *bx, u
 }
 
 template <int W, int K>
-__global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
+__global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
                                                       unsigned long long *counters, int64_t anchor_cap,
                                                       uint32_t *mz_hash, int32_t *mz_ctg, uint32_t *mz_pos,
                                                       int64_t mz_cap, int32_t mz_asm)
@@ -174,8 +133,6 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
     extern __shared__ __align__(16) unsigned char kb_scan_dyn[];  // the four per-warp queues (dynamic: the kernel needs > 48 KB in all)
     ScanQueue *queues = reinterpret_cast<ScanQueue *>(kb_scan_dyn);
     __shared__ int qtail[4];
-    __shared__ uint32_t stage_seq[4][32 * KB_SEQ_STRIDE];
-    __shared__ uint32_t stage_msk[4][32 * KB_MSK_STRIDE];
     __shared__ uint32_t window[4][4 * W * 32];  // bx, by, sx, sy: [slot][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *const bx = &window[warp][lane], *const by = bx + W * 32, *const sx = by + W * 32, *const sy = sx + W * 32;
@@ -199,42 +156,11 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
         if (lane == 0) tail = 0;
         __syncwarp();
 
-        // ---- loads: 4 x 16 B of sequence + 2 x 16 B of mask per lane, coalesced across the warp
-        uint32_t *sw = &stage_seq[warp][lane * KB_SEQ_STRIDE];
-        uint32_t *sm = &stage_msk[warp][lane * KB_MSK_STRIDE];
-        LaneFetch F;
-        F.w = sw, F.m = sm, F.base0 = lstart;
-        {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(bt.seq2 + ((soff + lstart) >> 4));
-            const uint4 *mp = reinterpret_cast<const uint4 *>(bt.nmask + ((soff + lstart) >> 5));
-            const bool in = lstart < clen;  // contig storage is padded to 128 bases: a started 64-base (sequence) or 128-base (mask) group is in bounds
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            uint4 v[4], mv[2];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) v[q4] = (in && lstart + q4 * 64 < clen) ? __ldg(sp + q4) : z;
-#pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) mv[q2] = (in && lstart + q2 * 128 < clen) ? __ldg(mp + q2) : z;
-            // look-back from the left neighbour (its last two sequence words / last mask word)
-            uint32_t p0 = __shfl_up_sync(0xffffffffu, v[3].z, 1);
-            uint32_t p1 = __shfl_up_sync(0xffffffffu, v[3].w, 1);
-            uint32_t pm = __shfl_up_sync(0xffffffffu, mv[1].w, 1);
-            if (lane == 0) {
-                if (cstart > 0) {
-                    const uint32_t *s1 = bt.seq2 + ((soff + lstart) >> 4);
-                    p0 = __ldg(s1 - 2), p1 = __ldg(s1 - 1);
-                    pm = __ldg(bt.nmask + ((soff + lstart) >> 5) - 1);
-                } else p0 = p1 = pm = 0;
-            }
-            sw[0] = p0, sw[1] = p1, sm[0] = pm;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-                sw[2 + q4 * 4 + 0] = v[q4].x, sw[2 + q4 * 4 + 1] = v[q4].y, sw[2 + q4 * 4 + 2] = v[q4].z, sw[2 + q4 * 4 + 3] = v[q4].w;
-#pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2)
-                sm[1 + q2 * 4 + 0] = mv[q2].x, sm[1 + q2 * 4 + 1] = mv[q2].y, sm[1 + q2 * 4 + 2] = mv[q2].z, sm[1 + q2 * 4 + 3] = mv[q2].w;
-        }
-        __syncwarp();
-
+        // ---- the lane's sequence / mask words: 16 bases (32 with the mask) per 32-bit load straight from global memory, one
+        // load per 16 (32) steps; gw[-2], gw[-1] and gm[-1] hold the 24-base look-back (the previous lane's last bases, or
+        // padding before the first base of a contig, which is replaced by "ambiguous" below)
+        const uint32_t *gw = bt.seq2 + ((soff + lstart) >> 4);
+        const uint32_t *gm = bt.nmask + ((soff + lstart) >> 5);
         // ---- sketch: all lanes step together; at most one regular minimizer per lane and step goes to the front of
         // the queue through a ballot (no atomics); the rare identical-k-mer emissions of mm_sketch go to the back of
         // the queue through a shared-memory counter.  The queue is drained whenever it holds >= 32 entries.
@@ -243,7 +169,9 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
 #pragma unroll
         for (int j = 0; j < W; ++j) bx[j * 32] = by[j * 32] = sx[j * 32] = sy[j * 32] = KB_MAXU;
         const bool active = lstart < lend;
-        const int p0pos = lstart >= KB_SCAN_LOOKBACK ? lstart - KB_SCAN_LOOKBACK : 0;
+        // every lane runs the same 24 silent look-back steps; before the first base of a contig they see ambiguous bases,
+        // which leave the sketch in its reset state (l = 0, empty window)
+        const int p0pos = lstart - KB_SCAN_LOOKBACK;
         const int i_end = active ? lend : 0;
         int front = 0;  // warp-uniform: entries pushed at the front of the queue
         auto slow = [&](uint32_t x, uint32_t y) {
@@ -258,11 +186,12 @@ __global__ void __launch_bounds__(128) kb_scan_kernel(KbIndexView ix, KbBatchVie
         for (int it = 0; it <= n_iter; ++it) {
             if (it < n_iter) {
                 for (int u = 0; u < W; ++u) {
-                    const int i = p0pos + it * W + u;
-                    const int r = i - lstart + 32;  // offset into the staged words (>= 8)
-                    if ((r & 15) == 0 || (it == 0 && u == 0)) word = sw[r >> 4] >> (2 * (r & 15));
-                    if ((r & 31) == 0 || (it == 0 && u == 0)) mword = sm[r >> 5] >> (r & 31);
-                    const int c = (mword & 1u) ? 4 : (int)(word & 3u);
+                    const int step = it * W + u;
+                    const int i = p0pos + step;
+                    const int r = step + 32 - KB_SCAN_LOOKBACK;  // offset of base i from the start of gw[-2]: the same in every lane
+                    if ((r & 15) == 0 || step == 0) word = i < i_end ? __ldg(gw + (r >> 4) - 2) >> (2 * (r & 15)) : 0u;
+                    if ((r & 31) == 0 || step == 0) mword = i < i_end ? __ldg(gm + (r >> 5) - 1) >> (r & 31) : 0u;
+                    const int c = ((mword & 1u) || i < 0) ? 4 : (int)(word & 3u);
                     word >>= 2, mword >>= 1;
                     uint32_t ex = 0, ey = 0;
                     bool e = false;
@@ -369,7 +298,7 @@ void kb_launch_scan(const KbIndexView &ix, const KbBatchView &bt, uint64_t *akey
 {
     if (bt.n_chunks == 0) return;
     int64_t want = (bt.n_chunks + 3) / 4;
-    int64_t grid = (int64_t)n_sm * 4;  // 4 CTAs of 128 threads (51 KB of shared memory each) per SM, grid-stride over the chunks
+    int64_t grid = (int64_t)n_sm * 6;  // 6 CTAs of 128 threads (36 KB of shared memory each) per SM, grid-stride over the chunks
     if (grid > want) grid = want;
     cudaFuncSetAttribute(kb_scan_kernel<10, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanQueue)));  // per device
     kb_scan_kernel<10, 15><<<(unsigned)grid, 128, 4 * sizeof(ScanQueue), st>>>(ix, bt, akey, aval, counters, anchor_cap, mz_hash, mz_ctg,
