@@ -19,6 +19,7 @@
 #define KB_EZ_RIGHT 0x2
 #define KB_EZ_REV_CIGAR 0x4
 #define KB_EZ_GLOBAL_NO_ZDROP 0x8
+#define KB_RING_WORDS 520       // 512 anti-diagonals + 8 alias words (a lane's 8 slots never wrap inside one step)
 
 struct KbAlignScratch {
     int32_t *dp;      // 11 * KB_DP_MAXLEN
@@ -29,7 +30,7 @@ struct KbAlignScratch {
     uint8_t *tfull;   // KB_TFULL_MAX target codes of [rs0, re0)
     uint32_t *cigar;  // KB_CIG_MAX, CIGAR of the hit being built
     uint32_t *ezcig;  // KB_CIG_MAX, CIGAR of the last DP
-    uint32_t *wmax;   // device only: 512-entry per-warp ring in shared memory (per-anti-diagonal maxima of kb_rows)
+    uint32_t *wmax;   // device only: per-warp ring of KB_RING_WORDS words in shared memory (per-anti-diagonal maxima of kb_rows)
 };
 
 KB_HD size_t kb_align_scratch_bytes(int64_t max_sw_cells)

@@ -491,10 +491,18 @@ __device__ __forceinline__ void kb_rows_cell(const KbC8 &c, int w, int d0, int n
     hd = hl, Hc[M] = z, hu = z;
     tbw[M >> 2] += d << (8 * (M & 3));
     if (TRACK) {
-        if (M < nvm && ok) {
-            const uint32_t key = (uint32_t)(z * 512 + (ckey - M));
-            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring + (((unsigned)(rbase + M) & 511u) << 2)), "r"(key) : "memory");
-        }
+        // `ring` is the byte address of the lane's slot-0 anti-diagonal in the ring (< 512 words in); slot M is M words on,
+        // possibly in the 8 alias words past the end, which drain() folds back
+        if (MASK) {
+            if (M < nvm && ok) {
+                const uint32_t key = (uint32_t)(z * 512 + (ckey - M));
+                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring + 4 * M), "r"(key) : "memory");
+            }
+        } else
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 k;\n\t"
+                         "setp.lt.s32 p, %3, %4;\n\tmad.lo.s32 k, %0, 512, %1;\n\t"
+                         "@p red.shared.max.u32 [%2+%5], k;\n\t}" ::"r"(z), "r"(ckey - M), "r"(ring), "n"(M), "r"(nvm), "n"(4 * M)
+                         : "memory");
     }
 }
 // One row of a lane's stripe.  A stripe of kact < 8 columns lives in the LAST kact slots, so the row is one jump
@@ -539,6 +547,14 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
         __syncwarp();
     }
     auto drain = [&](int r_lo) {  // fold ring entries of anti-diagonals [r_lo, r_lo + 512) into rmax[]
+        __syncwarp();
+        if (lane < 8) {  // alias words first: word 512 + x stands for word x
+            const uint32_t a = S.wmax[512 + lane];
+            if (a) {
+                S.wmax[512 + lane] = 0;
+                if (a > S.wmax[lane]) S.wmax[lane] = a;
+            }
+        }
         __syncwarp();
         for (int r = r_lo + lane; r < r_lo + 512; r += 32) {
             if (r < 0 || r >= n_diag) continue;
@@ -594,8 +610,9 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
                 const uint32_t sel = kb_score_sel(cq);
                 int32_t hu = uh, e1 = ue1, e2 = ue2, hd = dg;
                 uint32_t tbw[2];
-                if (any_edge) kb_rows_body<true, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
-                else kb_rows_body<false, TRACK>(c, kact, w, d0, nvm, ring, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
+                const unsigned rslot = ring + (((unsigned)(t0s + j) & 511u) << 2);
+                if (any_edge) kb_rows_body<true, TRACK>(c, kact, w, d0, nvm, rslot, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
+                else kb_rows_body<false, TRACK>(c, kact, w, d0, nvm, rslot, t0s + j, KB_ROWS_KEY_BIAS - t0s, sel, hu, e1, e2, hd, Hc, F1, F2, srow, tbw);
                 oh = hu, oe1 = e1, oe2 = e2;
                 uint32_t *dst = reinterpret_cast<uint32_t *>(tbt);  // a lane's slot is 8 bytes wide whatever kact is
                 kb_st_u32(dst + 1, tbw[1]);

@@ -189,10 +189,10 @@ __global__ void __launch_bounds__(128, KB_ALIGN_MINB) kb_align_kernel(KbIndexVie
     if (list) n_chains = (int64_t)*n_list;  // only the chains the staged path handed back
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    __shared__ uint32_t wmax_ring[4][512];
+    __shared__ uint32_t wmax_ring[4][KB_RING_WORDS];
     KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
     S.wmax = wmax_ring[threadIdx.x >> 5];
-    for (int x = lane; x < 512; x += 32) S.wmax[x] = 0;
+    for (int x = lane; x < KB_RING_WORDS; x += 32) S.wmax[x] = 0;
     __syncwarp();
     int64_t cells = 0;
     for (;;) {
@@ -373,12 +373,12 @@ __global__ void __launch_bounds__(128, KB_ROWS_MINB) kb_rows_kernel(KbIndexView 
                                                         size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
                                                         unsigned long long *counters)
 {
-    __shared__ uint32_t wmax_ring[4][512];
+    __shared__ uint32_t wmax_ring[4][KB_RING_WORDS];
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
     S.wmax = wmax_ring[threadIdx.x >> 5];
-    for (int x = lane; x < 512; x += 32) S.wmax[x] = 0;
+    for (int x = lane; x < KB_RING_WORDS; x += 32) S.wmax[x] = 0;
     __syncwarp();
     const KbDpConst P = kb_dp_const(ix.p);
     const long long n = (long long)counters[KB_SC_ROWS];
