@@ -62,6 +62,33 @@ def test_argument_errors_have_messages():
     assert b"max_gap" in L.kb_last_error()
 
 
+def test_documented_limits_are_reported_not_crossed():
+    """DESIGN.md section 3 limits: reported through kb_last_error before any device work (so checkable without a GPU)."""
+    L = _lib.load()
+    p = _lib.default_params()
+    h = C.c_void_p(0)
+    # > 32768 genes
+    n = 32769
+    g = np.frombuffer(b"ACGTACGTACGTACGTACGT" * n, dtype=np.uint8)
+    ln = np.full(n, 20, np.int32)
+    off = (np.arange(n, dtype=np.int64) * 20)
+    assert L.kb_index_create(_lib.ptr(g), _lib.ptr(off), _lib.ptr(ln), n, C.byref(p), 0, C.byref(h)) == -3
+    assert b"too many genes" in L.kb_last_error()
+    # other k / w than the compiled-in minimap2 defaults
+    p2 = _lib.default_params()
+    p2.k = 19
+    assert L.kb_index_create(_lib.ptr(g), _lib.ptr(off), _lib.ptr(ln), 4, C.byref(p2), 0, C.byref(h)) == -3
+    assert b"k=15" in L.kb_last_error()
+    # a gene minimizer that occurs in more than 2047 gene positions (one k-mer repeated over many genes)
+    unit = np.frombuffer(b"ACGGTCATTGCAAGCTTGACCATGCAAGTC", dtype=np.uint8)  # 30 bases, no internal repeat
+    n = 2100
+    g = np.tile(unit, n)
+    ln = np.full(n, len(unit), np.int32)
+    off = (np.arange(n, dtype=np.int64) * len(unit))
+    rc = L.kb_index_create(_lib.ptr(g), _lib.ptr(off), _lib.ptr(ln), n, C.byref(p), 0, C.byref(h))
+    assert rc == -3 and b"2047" in L.kb_last_error()
+
+
 def parse(data: bytes):
     import sys
 
