@@ -80,6 +80,30 @@ struct KbDirPack {  // 2-bit + mask packed contig bases, forwards or backwards f
     }
 };
 
+// sequential reader on top of an accessor: for the packed contigs it keeps the 32-base group it touched last (two sequence
+// words + one mask word), so a lane that walks along its diagonal pays three loads per 32 bases instead of two per base
+template <class S>
+struct KbSeqReader {
+    const S s;
+    __device__ __forceinline__ explicit KbSeqReader(const S &a) : s(a) {}
+    __device__ __forceinline__ int operator()(int x) { return s(x); }
+};
+template <>
+struct KbSeqReader<KbDirPack> {
+    const KbDirPack s;
+    int64_t grp = -1;
+    uint32_t w0 = 0, w1 = 0, mw = 0;
+    __device__ __forceinline__ explicit KbSeqReader(const KbDirPack &a) : s(a) {}
+    __device__ __forceinline__ int operator()(int x)
+    {
+        const int64_t b = s.pos + (int64_t)s.dir * x, g = b >> 5;
+        if (g != grp) grp = g, w0 = kb_ld_u32(s.seq2 + 2 * g), w1 = kb_ld_u32(s.seq2 + 2 * g + 1), mw = kb_ld_u32(s.nmask + g);
+        const int r = (int)(b & 31);
+        if ((mw >> r) & 1u) return 4;
+        return (int)(((r < 16 ? w0 : w1) >> (2 * (r & 15))) & 3u);
+    }
+};
+
 // constants of the x8 domain for one DP call
 struct KbC8 {
     int32_t oe1, oe2, of1, of2;  // open + first extension, with the tag of the state: -8 (q + e) + tag
@@ -251,6 +275,7 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
     if (margin < KB_BAND_MIN_MARGIN || (int64_t)32 * (r_end + 8) > P.max_sw_cells) return 0;
     const KbC8 c = kb_c8(P, 0);
     const int dlo = lo_d - margin, dhi = dlo + 63;
+    KbSeqReader<ST> tsr(ts);
     uint32_t *tbw = reinterpret_cast<uint32_t *>(S.tb);
     int32_t H1 = KB_NEG8, H2 = KB_NEG8, E1 = KB_NEG8, E2 = KB_NEG8, F1 = KB_NEG8, F2 = KB_NEG8;
     uint32_t acc = 0;
@@ -267,7 +292,7 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
             if (stepB) ++tp;
             else ++jp;
         }
-        srow = kb_score_row(P, c, ts((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1)));
+        srow = kb_score_row(P, c, tsr((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1)));
         sel = kb_score_sel(qs((jp < 1 ? 0 : (jp > qlen ? qlen : jp) - 1)));
         kb_band_step<true>(P, c, lane, stepB, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
@@ -279,7 +304,7 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
         kb_band_step<false>(P, c, lane, false, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
         ++tp;
-        srow = kb_score_row(P, c, ts((tp > tlen ? tlen : tp) - 1));
+        srow = kb_score_row(P, c, tsr((tp > tlen ? tlen : tp) - 1));
         kb_band_step<false>(P, c, lane, true, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if (((rp + 1) & 3) == 3) kb_st_u32(tbw + ((rp + 1) >> 2) * 32 + lane, acc);
     }
@@ -358,7 +383,8 @@ static __device__ __noinline__ int kb_global_bandK(const KbDpConst P, int lane, 
     for (int m = 0; m < K; ++m) H1[m] = H2[m] = E1[m] = E2[m] = F1[m] = F2[m] = KB_NEG8, srow[m] = sel[m] = 0;
     const int T0 = (dlo + 1) >> 1;  // T(0)
     int tp0 = T0 + lane * K, jp0 = -tp0;  // t', j' of the lane's slot 0 on anti-diagonal 0 (slot m: tp0 + m, jp0 - m)
-    auto tbase = [&](int tp) { return kb_score_row(P, c, ts((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1))); };
+    KbSeqReader<ST> tsr(ts);
+    auto tbase = [&](int tp) { return kb_score_row(P, c, tsr((tp < 1 ? 0 : (tp > tlen ? tlen : tp) - 1))); };
     auto qbase = [&](int jp) { return kb_score_sel(qs((jp < 1 ? 0 : (jp > qlen ? qlen : jp) - 1))); };
 #pragma unroll
     for (int m = 0; m < K; ++m) srow[m] = tbase(tp0 + m), sel[m] = qbase(jp0 - m);
