@@ -72,6 +72,17 @@ int kb_fasta_parse(const uint8_t *data, int64_t n, int64_t max_records,
                    int64_t *name_off, int32_t *name_len,
                    uint8_t *seq_out, int64_t seq_cap, int64_t *seq_off, int32_t *seq_len);
 
+/* Batch ingest: n_files FASTA buffers (one assembly each) parsed by n_threads host threads into the layout
+ * kb_map_assemblies / kb_batch_create take.  Replaces the reference's per-genome read + parse + copy (core/genome.py:45,
+ * core/seq.py:307-325) for batches.  Two-phase like the single-file calls: count per file, prefix-sum in the caller
+ * (rec_base / seq_base, n_files + 1 entries), then parse into caller buffers (seq_out may be pinned memory). */
+int kb_fasta_ingest_count(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads,
+                          int64_t *n_records, int64_t *n_seq_bytes);
+int kb_fasta_ingest_parse(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads,
+                          const int64_t *rec_base, const int64_t *seq_base, uint8_t *seq_out,
+                          int64_t *contig_off, int32_t *contig_len, int32_t *asm_contig_start,
+                          int64_t *name_off, int32_t *name_len);
+
 /* ---- gene index: the query side of map_batch (serotyping/core.py:111-121,154) ----
  * Built once per database; device-resident hash of every gene minimizer. */
 typedef struct kb_index kb_index_t;

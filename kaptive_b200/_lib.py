@@ -59,6 +59,8 @@ _SYMBOLS = [
     ("kb_device_count", C.c_int, []),
     ("kb_fasta_count", C.c_int, [_P, C.c_int64, _P, _P]),
     ("kb_fasta_parse", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
+    ("kb_fasta_ingest_count", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("kb_fasta_ingest_parse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("kb_index_create", C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(KbParams), C.c_int, C.POINTER(_P)]),
     ("kb_index_destroy", None, [_P]),
     ("kb_index_n_genes", C.c_int32, [_P]),

@@ -82,6 +82,16 @@ class AssemblyBatch:
         np.cumsum([len(a) for a in assemblies], out=acs[1:])
         return cls(data, off, ln, acs, device)
 
+    @classmethod
+    def from_fasta(cls, files: list[bytes], device: int = 0, threads: int | None = None) -> "AssemblyBatch":
+        """One assembly per FASTA buffer, parsed by the library's thread pool (``kaptive_b200.ingest``)."""
+        from . import ingest
+
+        b = ingest.ingest_fasta(files, threads=threads)
+        batch = cls(b.seqs if len(b.seqs) else np.zeros(1, np.uint8), b.contig_off, b.contig_len, b.asm_contig_start, device)
+        batch.contig_names = b.names
+        return batch
+
     @property
     def total_bases(self) -> int:
         return int(_lib.load().kb_batch_total_bases(self._h))

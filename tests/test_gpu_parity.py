@@ -292,3 +292,14 @@ def test_combined_k_and_o_database_and_fragmentation_ladder_equal_oracle(env):
         n_k += int((g < len(k.genes)).sum())
         n_o += int((g >= len(k.genes)).sum())
     assert n_k > 100 and n_o > 40
+
+
+def test_batch_fasta_ingest_feeds_the_mapper(env):
+    """FASTA bytes -> kb_fasta_ingest_* (host threads) -> kb_batch_create -> kb_map_batch gives the golden hits."""
+    names = ["fragmented", "lowercase", "n_rich", "empty_assembly", "two_loci"]
+    files = [cases.fasta_bytes(env["built"][n][1]) for n in names]
+    batch = env["mapper"].AssemblyBatch.from_fasta(files, threads=4)
+    assert [len(x) for x in batch.contig_names] == [sum(1 for _ in env["built"][n][1]) for n in names]
+    res = env["gi"].map(batch, fetch=True)
+    for ai, n in enumerate(names):
+        check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
