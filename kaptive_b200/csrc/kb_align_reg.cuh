@@ -236,6 +236,15 @@ __device__ __forceinline__ int kb_backtrack_warp(int lane, int i, int j, int rb,
 // statement of this argument (band pass vs full DP on random and tandem inputs); the GPU parity tests cover it end
 // to end.  Returns 1 when certified (ez complete, CIGAR in S.ezcig), 0 when the caller has to run the full DP.
 #define KB_BAND_MIN_MARGIN 8
+// any path leaving the band [dlo, dhi] scores at most this (see "Exactness" above)
+__device__ __forceinline__ int kb_band_bound64(const KbDpConst &P, int qlen, int tlen, int dlo, int dhi)
+{
+    const int d1 = tlen - qlen;
+    const int D_hi = dhi + 1, I_hi = D_hi - d1, I_lo = 1 - dlo, D_lo = I_lo + d1;
+    const int b_hi = (tlen - D_hi < 0 || qlen - I_hi < 0) ? KB_NEG_INF : P.a * (tlen - D_hi) - kb_gapcost2(P, D_hi) - kb_gapcost2(P, I_hi);
+    const int b_lo = (tlen - D_lo < 0 || qlen - I_lo < 0) ? KB_NEG_INF : P.a * (tlen - D_lo) - kb_gapcost2(P, D_lo) - kb_gapcost2(P, I_lo);
+    return b_hi > b_lo ? b_hi : b_lo;
+}
 template <bool EDGE>
 __device__ __forceinline__ void kb_band_step(const KbDpConst &P, const KbC8 &c, int lane, bool stepB, int tp, int jp, uint32_t srow,
                                              uint32_t sel, int32_t &H1, int32_t &H2, int32_t &E1, int32_t &E2, int32_t &F1, int32_t &F2,
@@ -298,6 +307,7 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
         if ((rp & 3) == 3) kb_st_u32(tbw + (rp >> 2) * 32 + lane, acc);
     }
     // interior: every in-range cell has real neighbours; cells past the far edges compute garbage nobody reads
+    const int cert_bound = kb_band_bound64(P, qlen, tlen, dlo, dhi);
     for (; rp + 1 <= r_end; rp += 2) {
         ++jp;
         sel = kb_score_sel(qs((jp > qlen ? qlen : jp) - 1));
@@ -307,6 +317,19 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
         srow = kb_score_row(P, c, tsr((tp > tlen ? tlen : tp) - 1));
         kb_band_step<false>(P, c, lane, true, tp, jp, srow, sel, H1, H2, E1, E2, F1, F2, acc);
         if (((rp + 1) & 3) == 3) kb_st_u32(tbw + ((rp + 1) >> 2) * 32 + lane, acc);
+        if (((rp >> 1) & 15) == 15) {
+            // give up early once the certificate is out of reach: a path ends on anti-diagonal rp or rp + 1 and gains at most
+            // +a per remaining column.  The score handed back is then an extrapolation (same loss per column for the rest),
+            // good enough to choose the wider window, whose own pass is certified on its real score.
+            const int m = __reduce_max_sync(0xffffffffu, H1 > H2 ? H1 : H2) >> 3;
+            const int rem = (r_end - rp + 1) >> 1;
+            if (m + P.a * rem <= cert_bound) {
+                const int done = (rp + 2) >> 1, loss = P.a * done - m;
+                ez.score = P.a * (done + rem) - (int)((int64_t)loss * (done + rem) / (done > 0 ? done : 1));
+                if (cell_counter && lane == 0) *cell_counter += (int64_t)32 * (rp + 2);
+                return 0;
+            }
+        }
     }
     if (rp == r_end) {
         ++jp;
@@ -317,14 +340,9 @@ static __device__ __noinline__ int kb_global_band(const KbDpConst P, int lane, i
     if ((r_end & 3) != 3) kb_st_u32(tbw + (r_end >> 2) * 32 + lane, acc >> (8 * (3 - (r_end & 3))));
     if (cell_counter && lane == 0) *cell_counter += (int64_t)32 * (r_end + 1);
     const int score = __shfl_sync(0xffffffffu, H1, (tlen - ((r_end + dlo + 1) >> 1)) & 31) >> 3;
-    {  // certificate
-        const int D_hi = dhi + 1, I_hi = D_hi - d1, I_lo = 1 - dlo, D_lo = I_lo + d1;
-        int b_hi = (tlen - D_hi < 0 || qlen - I_hi < 0) ? KB_NEG_INF : P.a * (tlen - D_hi) - kb_gapcost2(P, D_hi) - kb_gapcost2(P, I_hi);
-        int b_lo = (tlen - D_lo < 0 || qlen - I_lo < 0) ? KB_NEG_INF : P.a * (tlen - D_lo) - kb_gapcost2(P, D_lo) - kb_gapcost2(P, I_lo);
-        if (!(score > (b_hi > b_lo ? b_hi : b_lo))) {
-            ez.score = score;  // a valid alignment's score all the same: a lower bound for any wider band
-            return 0;
-        }
+    if (!(score > cert_bound)) {  // certificate
+        ez.score = score;  // a valid alignment's score all the same: a lower bound for any wider band
+        return 0;
     }
     __syncwarp();
     int bad = 0;
@@ -357,14 +375,9 @@ __device__ __forceinline__ bool kb_band_geometry(int qlen, int tlen, int K, int 
     dlo = lo_d - margin, dhi = dlo + 64 * K - 1;
     return margin >= KB_BAND_MIN_MARGIN;
 }
-// any path leaving the band [dlo, dhi] scores at most this
 __device__ __forceinline__ int kb_band_bound(const KbDpConst &P, int qlen, int tlen, int dlo, int dhi)
 {
-    const int d1 = tlen - qlen;
-    const int D_hi = dhi + 1, I_hi = D_hi - d1, I_lo = 1 - dlo, D_lo = I_lo + d1;
-    const int b_hi = (tlen - D_hi < 0 || qlen - I_hi < 0) ? KB_NEG_INF : P.a * (tlen - D_hi) - kb_gapcost2(P, D_hi) - kb_gapcost2(P, I_hi);
-    const int b_lo = (tlen - D_lo < 0 || qlen - I_lo < 0) ? KB_NEG_INF : P.a * (tlen - D_lo) - kb_gapcost2(P, D_lo) - kb_gapcost2(P, I_lo);
-    return b_hi > b_lo ? b_hi : b_lo;
+    return kb_band_bound64(P, qlen, tlen, dlo, dhi);
 }
 
 template <int K, class SQ, class ST>

@@ -357,6 +357,12 @@ __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView 
                 ok = k2 == 2 ? kb_global_bandK<2>(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells)
                              : kb_global_bandK<4>(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
                 if (lane == 0) KB_DP_STAT(2, ok ? 0 : 1, (int64_t)32 * k2 * (J->qlen + J->tlen + 1));
+                // the first pass may have handed back an extrapolated score: a rejected 128-diagonal pass gets one more try
+                if (!ok && k2 == 2 && 64 * 4 * 3 <= 2 * (J->qlen + J->tlen) && kb_band_geometry(J->qlen, J->tlen, 4, dlo, dhi) &&
+                    ez.score > kb_band_bound(P, J->qlen, J->tlen, dlo, dhi)) {
+                    ok = kb_global_bandK<4>(P, lane, J->qlen, sq, J->tlen, st, J->flag, ez, S, &cells);
+                    if (lane == 0) KB_DP_STAT(2, ok ? 0 : 1, (int64_t)32 * 4 * (J->qlen + J->tlen + 1));
+                }
             }
         }
         if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
