@@ -172,7 +172,24 @@ KB_HD int kb_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, int ge
         if (J.state != 1 || J.n_cigar < 0 || J.zdropped) return -1;
         const KbByteSeq qseq{qseq0 + J.qoff};
         const KbPackSeq tseq{bt.seq2, bt.nmask, J.tpos};
-        if (kb_test_zdrop(P, qseq, tseq, J.n_cigar, jobcig + J.cigar_off) != 0) return -1;
+        // mm_test_zdrop walks the alignment base by base; it cannot fire when everything the walk can lose stays within
+        // the threshold: its drop is at most the sum of the negative steps, i.e. at most
+        // sum over M columns of (a - column score) + sum over gaps of (q + e len)
+        //   = a * M_total - (score + sum of dual-affine gap costs) + sum of single-affine gap costs.
+        {
+            const uint32_t *cg = jobcig + J.cigar_off;
+            int64_t m_tot = 0, g1 = 0, g2 = 0;
+            for (int k = 0; k < J.n_cigar; ++k) {
+                const int64_t len = cg[k] >> 4;
+                if ((cg[k] & 0xf) == 0) m_tot += len;
+                else {
+                    const int64_t c1 = P.q + P.e * len, c2 = P.q2 + P.e2 * len;
+                    g1 += c1, g2 += c1 < c2 ? c1 : c2;
+                }
+            }
+            if (P.a * m_tot - ((int64_t)J.score + g2) + g1 > P.zdrop)
+                if (kb_test_zdrop(P, qseq, tseq, J.n_cigar, jobcig + J.cigar_off) != 0) return -1;
+        }
         if (J.n_cigar > 0) {
             kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
             r.has_p = 1;
