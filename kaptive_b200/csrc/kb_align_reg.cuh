@@ -675,29 +675,53 @@ static __device__ __noinline__ void kb_rows(const KbDpConst P, int lane, int qle
     }
     KbEz z_;
     z_.max = 0, z_.max_q = z_.max_t = -1, z_.score = KB_NEG_INF, z_.zdropped = 0, z_.n_cigar = 0;
-    if (TRACK) {  // [mm2:ksw2.h:ksw_apply_zdrop] over the per-anti-diagonal maxima, in order
-        int zd = 0, mx = 0, mt = -1, mq = -1;
-        if (lane == 0) {
-            for (int r = 0; r < n_diag; ++r) {
-                const uint32_t key = rmax[r];
-                if (key == 0) {  // empty anti-diagonal (band excludes it): the spec stops here
-                    zd = 1;
-                    break;
-                }
+    if (TRACK) {
+        // [mm2:ksw2.h:ksw_apply_zdrop] over the per-anti-diagonal maxima, in order.  The running state (max so far, first cell
+        // attaining it) before anti-diagonal r is a prefix maximum, so every lane takes a contiguous chunk of r: pass 1 finds
+        // the chunk's first maximum, a warp scan turns that into the state at the chunk's start, pass 2 replays the chunk with
+        // the exact rule and reports the first anti-diagonal where the spec stops (z-drop, or an anti-diagonal the band leaves
+        // empty); the earliest one over the warp wins.
+        const int chunk = (n_diag + 31) >> 5, lo = lane * chunk, hi = lo + chunk < n_diag ? lo + chunk : n_diag;
+        int lmx = INT32_MIN, lr = -1, lt = 0;
+        for (int r = lo; r < hi; ++r) {
+            const uint32_t key = rmax[r];
+            if (key == 0) continue;
+            const int32_t h = (int32_t)(key >> 12) - (1 << 19);
+            if (h > lmx) lmx = h, lr = r, lt = 4095 - (int32_t)(key & 4095u);
+        }
+        int smx = lmx, sr = lr, st = lt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int omx = __shfl_up_sync(0xffffffffu, smx, d), orr = __shfl_up_sync(0xffffffffu, sr, d), ot = __shfl_up_sync(0xffffffffu, st, d);
+            if (lane >= d && omx >= smx) smx = omx, sr = orr, st = ot;  // the earlier chunk wins ties: first occurrence
+        }
+        int pmx = __shfl_up_sync(0xffffffffu, smx, 1), pr = __shfl_up_sync(0xffffffffu, sr, 1), pt = __shfl_up_sync(0xffffffffu, st, 1);
+        if (lane == 0) pmx = INT32_MIN;
+        int mx = 0, mt = -1, mq = -1;
+        if (pmx > 0) mx = pmx, mt = pt, mq = pr - pt;
+        int stop = INT32_MAX, bmx = 0, bmt = -1, bmq = -1;
+        for (int r = lo; r < hi; ++r) {
+            const uint32_t key = rmax[r];
+            bool brk = key == 0;  // empty anti-diagonal (band excludes it): the spec stops here
+            if (!brk) {
                 const int32_t max_H = (int32_t)(key >> 12) - (1 << 19), max_t = 4095 - (int32_t)(key & 4095u);
                 if (max_H > mx) mx = max_H, mt = max_t, mq = r - max_t;
                 else if (max_t >= mt && r - max_t >= mq) {
                     const int tl = max_t - mt, ql = (r - max_t) - mq, l = tl > ql ? tl - ql : ql - tl;
-                    if (zdrop >= 0 && mx - max_H > zdrop + l * P.e2) {
-                        zd = 1;
-                        KB_DP_STAT_RAW(30, 1), KB_DP_STAT_RAW(31, (int64_t)r * 1000 / n_diag);
-                        break;
-                    }
+                    brk = zdrop >= 0 && mx - max_H > zdrop + l * P.e2;
+                    if (brk) KB_DP_STAT_RAW(30, 1), KB_DP_STAT_RAW(31, (int64_t)r * 1000 / n_diag);
                 }
             }
+            if (brk) {
+                stop = r, bmx = mx, bmt = mt, bmq = mq;
+                break;
+            }
         }
-        z_.zdropped = __shfl_sync(0xffffffffu, zd, 0), z_.max = __shfl_sync(0xffffffffu, mx, 0);
-        z_.max_t = __shfl_sync(0xffffffffu, mt, 0), z_.max_q = __shfl_sync(0xffffffffu, mq, 0);
+        const int first = __reduce_min_sync(0xffffffffu, stop);
+        int owner = 31;  // no stop: the state after the last chunk
+        if (first != INT32_MAX) owner = __ffs(__ballot_sync(0xffffffffu, stop == first)) - 1, mx = bmx, mt = bmt, mq = bmq;
+        z_.zdropped = first != INT32_MAX;
+        z_.max = __shfl_sync(0xffffffffu, mx, owner), z_.max_t = __shfl_sync(0xffffffffu, mt, owner), z_.max_q = __shfl_sync(0xffffffffu, mq, owner);
     }
     if (!z_.zdropped) z_.score = score;
     if (cell_counter && lane == 0) *cell_counter += (int64_t)qlen * tlen;

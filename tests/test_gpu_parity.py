@@ -303,3 +303,14 @@ def test_batch_fasta_ingest_feeds_the_mapper(env):
     res = env["gi"].map(batch, fetch=True)
     for ai, n in enumerate(names):
         check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
+
+
+def test_one_warp_per_chain_kernel_alone_gives_the_same_hits(env, monkeypatch):
+    """KAPTIVE_B200_STAGED=0 sends every chain through kb_align_kernel (all of mm_align1 in one warp), the kernel that
+    otherwise only serves the chains the staged path hands back: it has to stay bit-identical."""
+    monkeypatch.setenv("KAPTIVE_B200_STAGED", "0")
+    names = ["mutated1", "divergent", "big_indel", "mosaic_gene", "boundaries"]
+    res = env["gi"].map_contigs([[s for _, s in env["built"][n][1]] for n in names])
+    assert res.counters["slow_chains"] == 0  # the staged path did not run at all
+    for ai, n in enumerate(names):
+        check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
