@@ -551,7 +551,10 @@ KB_HD void kb_append_cigar(KbReg &r, uint32_t *cigar, int n_cigar, const uint32_
 }
 
 // minimap2 align.c mm_fix_cigar + mm_update_extra (lane 0 only)
-template <class SQ, class ST>
+// FLAT = true walks the alignment as ONE loop over its columns (a small state machine over the CIGAR) instead of nested
+// per-operation loops: same arithmetic in the same order, but when one GPU thread per chain runs it (kb_assemble_kernel) the
+// lanes of a warp stay in step instead of serialising each other's inner loops.
+template <bool FLAT = false, class SQ, class ST>
 KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, SQ qseq, ST tseq)
 {
     int32_t toff = 0, qoff = 0, to_shrink = 0, qshift = 0, tshift = 0;
@@ -622,6 +625,44 @@ KB_HD void kb_update_extra(const kb_params_t &P, KbReg &r, uint32_t *cigar, SQ q
     toff = qoff = 0;
     double s = 0.0, mx = 0.0;
     r.blen = r.mlen = 0, r.n_ambi = 0;
+    if (FLAT) {
+        KB_WARP_RECONVERGE();  // FLAT is the one-thread-per-chain caller: every lane of the warp gets here (kb_stage_assemble)
+        int32_t blen = 0, mlen = 0, n_ambi = 0;
+        uint32_t op = 3, rem = 0;
+        k = -1;
+        for (;;) {
+            if (rem == 0) {
+                if (++k >= r.n_cigar) break;
+                op = cigar[k] & 0xf, rem = cigar[k] >> 4;
+                if (op == 1 || op == 2) {  // the gap's penalty does not depend on its bases: applied when the gap is entered
+                    double pen = kb_dmul((double)P.e, (double)kb_log2_fast((float)(1.0 + rem)));
+                    pen = kb_dadd((double)P.q, pen);
+                    s = kb_dadd(s, -pen);
+                    if (s < 0) s = 0;
+                } else if (op != 0) rem = 0;
+                continue;
+            }
+            if (op == 0) {
+                const int cq = qseq[qoff], ct = tseq[toff];
+                const bool amb = ct > 3 || cq > 3, diff = !amb && ct != cq;
+                s = kb_dadd(s, amb ? (double)-P.sc_ambi : (diff ? (double)-P.b : (double)P.a));
+                if (s < 0) s = 0;
+                else mx = mx > s ? mx : s;
+                n_ambi += amb, blen += !amb, mlen += !(amb || diff);
+                ++qoff, ++toff;
+            } else if (op == 1) {
+                const bool amb = qseq[qoff] > 3;
+                n_ambi += amb, blen += !amb, ++qoff;
+            } else {
+                const bool amb = tseq[toff] > 3;
+                n_ambi += amb, blen += !amb, ++toff;
+            }
+            --rem;
+        }
+        r.blen = blen, r.mlen = mlen, r.n_ambi = n_ambi;
+        r.dp_max = (int32_t)kb_dadd(mx, .499);
+        return;
+    }
     for (k = 0; k < r.n_cigar; ++k) {
         uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
         if (op == 0) {

@@ -16,6 +16,15 @@
 #define KB_D inline
 #endif
 
+// Re-converge the lanes of a warp (device only).  One-thread-per-item kernels run long data-dependent loops; lanes that
+// left an earlier loop at different times are not guaranteed to meet again before the next one unless told to.  Every
+// lane of the warp that has not exited must reach the same call.
+#ifdef __CUDA_ARCH__
+#define KB_WARP_RECONVERGE() __syncwarp()
+#else
+#define KB_WARP_RECONVERGE() ((void)0)
+#endif
+
 #define KB_MAXU 0xffffffffu
 #define KB_SEED_LONG_JOIN (1ULL << 40)
 #define KB_SEED_IGNORE (1ULL << 41)

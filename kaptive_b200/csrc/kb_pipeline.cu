@@ -430,8 +430,9 @@ __global__ void __launch_bounds__(128) kb_assemble_kernel(KbIndexView ix, KbBatc
     r.as = c.as, r.cnt = c.cnt, r.score = c.score, r.score0 = c.score0, r.mlen = c.mlen, r.blen = c.blen, r.parent = c.parent, r.id = reg_idx;
     r.hash = c.hash, r.rev = c.rev, r.rid = c.rid, r.rs = c.rs, r.re = c.re, r.qs = c.qs, r.qe = c.qe;
     r.has_p = 0, r.dp_score = 0, r.dp_max = 0, r.n_ambi = 0, r.n_cigar = 0;
-    int rc = -1;
-    if (toff + total + 1 <= tmpcig_cap) rc = kb_stage_assemble(ix, bt, gi.gene, pl, J, jobcig, r, tmpcig + toff);
+    // every lane that got here calls it (it contains the warp's re-convergence point); one without scratch room is disabled
+    const bool room = toff + total + 1 <= tmpcig_cap;
+    const int rc = kb_stage_assemble(ix, bt, gi.gene, pl, J, jobcig, r, tmpcig + (room ? toff : 0), room);
     if (rc != 0) {
         slow_list[atomicAdd(&counters[KB_SC_SLOW], 1ull)] = (int32_t)ci;
         return;

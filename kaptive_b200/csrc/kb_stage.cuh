@@ -148,28 +148,36 @@ struct KbJobWrite {  // sink that stores job k at out[k]
 // when r (and cig[0 .. r.n_cigar)) is exactly what kb_align1 produces for the chain, or -1 when the chain has to be
 // redone by kb_align1 (z-drop in a fill, DP error).
 KB_HD int kb_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, int gene, const KbPlan &pl, const KbJob *jobs,
-                            const uint32_t *jobcig, KbReg &r, uint32_t *cig)
+                            const uint32_t *jobcig, KbReg &r, uint32_t *cig, bool enabled = true)
 {
+    // Single exit on purpose: on the GPU one thread per chain runs this and every lane of a warp -- also the ones whose
+    // chain has already failed (rc != 0) or that have nothing to do (!enabled) -- walks down to the re-convergence point
+    // inside kb_update_extra<true>, so that the long per-column loop there is executed by the whole warp in step.
     const kb_params_t &P = ix.p;
     const uint8_t *qseq0 = (pl.rev ? ix.gseq_rev : ix.gseq_fwd) + ix.gene_seq_off[gene];
-    int jb = 0;
-    int32_t rs1, qs1, re1, qe1;
+    int jb = 0, rc = enabled ? 0 : -1;
+    int32_t rs1 = pl.rs, qs1 = pl.qs, re1 = pl.re, qe1 = pl.qe;
     r.has_p = 0, r.dp_score = 0, r.dp_max = 0, r.n_ambi = 0, r.n_cigar = 0;
-    if (pl.has_left) {
+    if (rc == 0 && pl.has_left) {
         const KbJob &J = jobs[jb++];
-        if (J.state != 1 || J.n_cigar < 0) return -1;
-        if (J.n_cigar > 0) {
-            kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
-            r.has_p = 1;
-            r.dp_score += J.max;
+        if (J.state != 1 || J.n_cigar < 0) rc = -1;
+        else {
+            if (J.n_cigar > 0) {
+                kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
+                r.has_p = 1;
+                r.dp_score += J.max;
+            }
+            rs1 = pl.rs - (J.max_t + 1);
+            qs1 = pl.qs - (J.max_q + 1);
         }
-        rs1 = pl.rs - (J.max_t + 1);
-        qs1 = pl.qs - (J.max_q + 1);
-    } else rs1 = pl.rs, qs1 = pl.qs;
-    const int n_fill = pl.n_jobs - pl.has_left - pl.has_right;
-    for (int f = 0; f < n_fill; ++f) {
+    }
+    const int n_fill = enabled ? pl.n_jobs - pl.has_left - pl.has_right : 0;
+    for (int f = 0; f < n_fill && rc == 0; ++f) {
         const KbJob &J = jobs[jb++];
-        if (J.state != 1 || J.n_cigar < 0 || J.zdropped) return -1;
+        if (J.state != 1 || J.n_cigar < 0 || J.zdropped) {
+            rc = -1;
+            break;
+        }
         const KbByteSeq qseq{qseq0 + J.qoff};
         const KbPackSeq tseq{bt.seq2, bt.nmask, J.tpos};
         // mm_test_zdrop walks the alignment base by base; it cannot fire when everything the walk can lose stays within
@@ -188,7 +196,10 @@ KB_HD int kb_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, int ge
                 }
             }
             if (P.a * m_tot - ((int64_t)J.score + g2) + g1 > P.zdrop)
-                if (kb_test_zdrop(P, qseq, tseq, J.n_cigar, jobcig + J.cigar_off) != 0) return -1;
+                if (kb_test_zdrop(P, qseq, tseq, J.n_cigar, jobcig + J.cigar_off) != 0) {
+                    rc = -1;
+                    break;
+                }
         }
         if (J.n_cigar > 0) {
             kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
@@ -196,21 +207,24 @@ KB_HD int kb_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, int ge
         }
         r.dp_score += J.score;
     }
-    if (pl.has_right) {
+    if (rc == 0 && pl.has_right) {
         const KbJob &J = jobs[jb++];
-        if (J.state != 1 || J.n_cigar < 0) return -1;
-        if (J.n_cigar > 0) {
-            kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
-            r.has_p = 1;
-            r.dp_score += J.max;
+        if (J.state != 1 || J.n_cigar < 0) rc = -1;
+        else {
+            if (J.n_cigar > 0) {
+                kb_append_cigar(r, cig, J.n_cigar, jobcig + J.cigar_off);
+                r.has_p = 1;
+                r.dp_score += J.max;
+            }
+            re1 = pl.re + (J.max_t + 1);
+            qe1 = pl.qe + (J.max_q + 1);
         }
-        re1 = pl.re + (J.max_t + 1);
-        qe1 = pl.qe + (J.max_q + 1);
-    } else re1 = pl.re, qe1 = pl.qe;
-    if (r.n_cigar > KB_CIG_MAX) return -1;
+    }
+    if (rc == 0 && r.n_cigar > KB_CIG_MAX) rc = -1;
+    if (rc != 0) r.n_cigar = 0, r.has_p = 0;  // the walk below then has nothing to do, but is still entered by this lane
     r.rs = rs1, r.re = re1;
     if (pl.rev) r.qs = pl.qlen - qe1, r.qe = pl.qlen - qs1;
     else r.qs = qs1, r.qe = qe1;
-    if (r.has_p) kb_update_extra(P, r, cig, KbByteSeq{qseq0 + qs1}, KbPackSeq{bt.seq2, bt.nmask, pl.soff + rs1});
-    return 0;
+    kb_update_extra<true>(P, r, cig, KbByteSeq{qseq0 + qs1}, KbPackSeq{bt.seq2, bt.nmask, pl.soff + rs1});
+    return rc;
 }
