@@ -33,7 +33,7 @@ size_t kb_rle_temp_bytes(int64_t);
 cudaError_t kb_rle(void *, size_t, const uint32_t *, uint32_t *, uint32_t *, int64_t *, int64_t, cudaStream_t);
 void kb_launch_chain(const KbIndexView &, const KbBatchView &, const uint64_t *, const uint32_t *, const int64_t *, int64_t, int64_t,
                      const uint16_t *, const int32_t *, const KbChainWork &, uint64_t *, uint64_t *, KbGroupInfo *, KbChainRec *,
-                     unsigned long long *, int64_t, cudaStream_t);
+                     unsigned long long *, int64_t, const int32_t *, cudaStream_t);
 void kb_launch_align(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
                      uint64_t *, uint8_t *, size_t, int, KbRawHit *, int64_t, uint32_t *, int64_t, unsigned long long *,
                      unsigned long long *, const int32_t *, const unsigned long long *, cudaStream_t);
@@ -526,6 +526,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
 
         // ---------------- occurrence counts, census where needed
         std::vector<int32_t> mid_occ((size_t)n_asm, p.mid_occ > 0 ? p.mid_occ : p.min_mid_occ);
+        std::vector<int32_t> occ_skip((size_t)n_asm + 1, 0);
         size_t occ_words = ((size_t)n_asm * (size_t)iv.n_entries + 1) / 2 + 4;
         uint32_t *occ32 = P.get<uint32_t>(occ_words);
         int32_t *d_need = P.get<int32_t>((size_t)n_asm + 1);
@@ -540,6 +541,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             CU(cudaStreamSynchronize(st));
             const char *fc = getenv("KAPTIVE_B200_FORCE_CENSUS");
             bool force = (fc && fc[0] == '1') || ix->host.max_qocc > p.min_mid_occ;
+            for (int a = 0; a < n_asm; ++a) occ_skip[(size_t)a] = need[(size_t)a] == 0 && mid_occ[(size_t)a] >= p.min_mid_occ;
             for (int a = 0; a < n_asm; ++a) {
                 if (need[(size_t)a] == 2) throw std::string("a gene minimizer occurs more than 65519 times in one assembly (limit)");
                 if (p.mid_occ <= 0 && (need[(size_t)a] || force)) {
@@ -550,6 +552,10 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         }
         int32_t *d_mid = P.get<int32_t>((size_t)n_asm + 1);
         CU(cudaMemcpyAsync(d_mid, mid_occ.data(), (size_t)n_asm * 4, cudaMemcpyHostToDevice, st));
+        // assemblies in which no gene minimizer occurs more than min_mid_occ times (and whose mid_occ is not below that floor):
+        // the occurrence filter cannot fire there, the chain kernel skips its table look-ups
+        int32_t *d_occ_skip = P.get<int32_t>((size_t)n_asm + 1);
+        CU(cudaMemcpyAsync(d_occ_skip, occ_skip.data(), (size_t)n_asm * 4, cudaMemcpyHostToDevice, st));
         R->mid_occ = mid_occ;
 
         // ---------------- sort anchors by (asm, gene, strand, position)
@@ -593,7 +599,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         int64_t chain_cap = n_anchors / 3 + 16;
         KbChainRec *chains = P.get<KbChainRec>((size_t)chain_cap);
         kb_launch_chain(iv, bv, skey, sval, gstart, n_groups, n_anchors, (const uint16_t *)occ32, d_mid, W, cx, cy, ginfo, chains,
-                        d_counters, chain_cap, st);
+                        d_counters, chain_cap, d_occ_skip, st);
         ++launches;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));

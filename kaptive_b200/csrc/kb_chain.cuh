@@ -205,8 +205,10 @@ struct KbChainRegView : KbChainRec {
 KB_HD int kb_chain_group(const KbIndexView &ix, const KbBatchView &bt, const uint64_t *akey, const uint32_t *aval,
                          int64_t gs, int64_t ge, const uint16_t *occ, const int32_t *mid_occ_arr, KbChainWork W,
                          uint64_t *cx_, uint64_t *cy_, KbGroupInfo *gi, KbChainRec *chains, unsigned long long *chain_counter,
-                         int64_t chain_cap, int32_t group_id)
+                         int64_t chain_cap, int32_t group_id, const int32_t *occ_skip = nullptr)
 {
+    // occ_skip[asm] != 0: no gene minimizer occurs more often in this assembly than the mid_occ in force, so the per-anchor
+    // look-up in the (large, randomly addressed) occurrence table cannot filter anything and is skipped
     const kb_params_t &P = ix.p;
     const int32_t asm_id = (int32_t)(akey[gs] >> KB_KEY_ASM_SHIFT);
     const int32_t gene = (int32_t)(akey[gs] >> KB_KEY_GENE_SHIFT) & (KB_MAX_GENES - 1);
@@ -214,6 +216,7 @@ KB_HD int kb_chain_group(const KbIndexView &ix, const KbBatchView &bt, const uin
     const int32_t mid = mid_occ_arr[asm_id];
     const int32_t K = P.k;
     const bool qflt = nmin > mid && P.q_occ_frac > 0.0f && mid > 0;
+    const bool skip_occ = occ_skip && occ_skip[asm_id];
     uint32_t *x = W.x + gs;
     int32_t *y = W.y + gs, *f = W.f + gs, *p = W.p + gs, *v = W.v + gs, *t = W.t + gs;
     uint64_t *z = W.z + gs, *u = W.u + gs, *cx = cx_ + gs, *cy = cy_ + gs;
@@ -226,7 +229,7 @@ KB_HD int kb_chain_group(const KbIndexView &ix, const KbBatchView &bt, const uin
         uint32_t e = aval[i];
         KbEntry en = ix.ent[e];
         if (qflt && en.qocc > mid && (float)en.qocc > kb_fmul((float)nmin, P.q_occ_frac)) continue;
-        int32_t occ_n = occ[(int64_t)asm_id * ix.n_entries + e];
+        const int32_t occ_n = skip_occ ? 0 : occ[(int64_t)asm_id * ix.n_entries + e];
         if (occ_n > mid) {
             t[n_rep++] = (int32_t)(en.qpos_z >> 1);  // t[] is free until chaining starts; n_rep <= i - gs - n
             continue;

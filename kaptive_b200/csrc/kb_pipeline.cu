@@ -158,22 +158,22 @@ __global__ void __launch_bounds__(128) kb_chain_kernel(KbIndexView ix, KbBatchVi
                                                        const int64_t *gstart, int64_t n_groups, int64_t n_anchors,
                                                        const uint16_t *occ, const int32_t *mid_occ, KbChainWork W, uint64_t *cx,
                                                        uint64_t *cy, KbGroupInfo *ginfo, KbChainRec *chains,
-                                                       unsigned long long *counters, int64_t chain_cap)
+                                                       unsigned long long *counters, int64_t chain_cap, const int32_t *occ_skip)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     int64_t gs = gstart[g], ge = g + 1 < n_groups ? gstart[g + 1] : n_anchors;
-    kb_chain_group(ix, bt, skey, sval, gs, ge, occ, mid_occ, W, cx, cy, &ginfo[g], chains, &counters[3], chain_cap, (int32_t)g);
+    kb_chain_group(ix, bt, skey, sval, gs, ge, occ, mid_occ, W, cx, cy, &ginfo[g], chains, &counters[3], chain_cap, (int32_t)g, occ_skip);
 }
 
 void kb_launch_chain(const KbIndexView &ix, const KbBatchView &bt, const uint64_t *skey, const uint32_t *sval, const int64_t *gstart,
                      int64_t n_groups, int64_t n_anchors, const uint16_t *occ, const int32_t *mid_occ, const KbChainWork &W,
                      uint64_t *cx, uint64_t *cy, KbGroupInfo *ginfo, KbChainRec *chains, unsigned long long *counters,
-                     int64_t chain_cap, cudaStream_t st)
+                     int64_t chain_cap, const int32_t *occ_skip, cudaStream_t st)
 {
     if (n_groups <= 0) return;
     kb_chain_kernel<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(ix, bt, skey, sval, gstart, n_groups, n_anchors, occ, mid_occ,
-                                                                        W, cx, cy, ginfo, chains, counters, chain_cap);
+                                                                        W, cx, cy, ginfo, chains, counters, chain_cap, occ_skip);
 }
 
 // ------------------------------------------------------------------ alignment: one warp per chain, persistent
