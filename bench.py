@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--n-loci", type=int, default=150)
     ap.add_argument("--genes-per-locus", type=int, default=20)
     ap.add_argument("--n-core", type=int, default=4)
-    ap.add_argument("--e2e-asm", type=int, default=512, help="assemblies per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-asm", type=int, default=1000, help="assemblies per end-to-end step (host buffers)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

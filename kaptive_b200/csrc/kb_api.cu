@@ -888,21 +888,25 @@ static int map_assemblies_once(const kb_index_t *ix, const uint8_t *contig_seqs,
     return rc;
 }
 
-// Host buffers in, host arrays out.  Inputs beyond one slab (1024 assemblies unless KAPTIVE_B200_SLAB says otherwise)
-// are cut into slabs that two host threads push through batch_create -> map on their own streams, which bounds the
-// device memory of a call and lets the H2D copy and packing of one slab overlap the kernels of the other; the slabs'
-// hits are then fetched in assembly order.  Slabs must stay large: measured on B200, 32-64 assembly slabs lose more
-// to half-empty persistent kernels than the overlap wins (scripts/e2e_probe.py).  Results do not depend on the slab
-// size (assemblies are independent units; tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
+// Host buffers in, host arrays out.  Calls of 512 assemblies or more are cut into equal slabs (at least two, at most
+// KAPTIVE_B200_SLAB = 768 assemblies each) that two host threads push through batch_create -> map on their own streams, which
+// bounds the device memory of a call and lets the H2D copy and packing of one slab overlap the kernels of the other; the
+// slabs' hits are then fetched in assembly order.  Slabs must stay large: measured on B200 (scripts/e2e_probe.py, 1000
+// assemblies per call) one slab takes 418 ms, two 382 ms, four 390 ms, six on three threads 440 ms and more -- small slabs
+// lose more to half-empty persistent kernels than the overlap wins.  Results do not depend on the slab size (assemblies
+// are independent units; tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
 int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
                       const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
                       int64_t cigar_cap, int64_t *n_cigar)
 {
     if (!ix) return fail(KB_ERR_ARG, "null index");
     if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
-    int slab = 1024;
-    if (const char *e = getenv("KAPTIVE_B200_SLAB")) slab = atoi(e) > 0 ? atoi(e) : slab;
-    const int n_slabs = n_asm <= slab + slab / 2 ? 1 : (n_asm + slab - 1) / slab;
+    int slab = 768, n_slabs;
+    if (const char *e = getenv("KAPTIVE_B200_SLAB")) {  // explicit slab size: cut whenever the call is larger
+        slab = atoi(e) > 0 ? atoi(e) : slab;
+        n_slabs = n_asm <= slab ? 1 : (n_asm + slab - 1) / slab;
+    } else n_slabs = n_asm < 512 ? 1 : std::max(2, (n_asm + slab - 1) / slab);
+    if (n_slabs > 1) slab = (n_asm + n_slabs - 1) / n_slabs;  // equal slabs
     std::vector<kb_result_t *> res((size_t)n_slabs, nullptr);
     std::vector<int> rcs((size_t)n_slabs, KB_OK);
     std::vector<std::string> errs((size_t)n_slabs);
@@ -921,7 +925,9 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
             for (int k; (k = next.fetch_add(1)) < n_slabs;) run_slab(k);
         };
         std::vector<std::thread> th;
-        for (int t = 0; t < std::min(2, n_slabs); ++t) th.emplace_back(worker);
+        int n_thr = 2;
+        if (const char *e = getenv("KAPTIVE_B200_SLAB_THREADS")) n_thr = atoi(e) > 0 ? atoi(e) : n_thr;
+        for (int t = 0; t < std::min(n_thr, n_slabs); ++t) th.emplace_back(worker);
         for (auto &t : th) t.join();
     }
     int rc = KB_OK;

@@ -20,12 +20,12 @@ for rep in range(4):
     r = gi.map(b, fetch=True)
     t2 = time.perf_counter()
     print(f"n={n} batch_create {1e3*(t1-t0):.1f} ms ({n*5e6/(t1-t0)/1e9:.1f} GB/s)  map+fetch {1e3*(t2-t1):.1f} ms  stages {r.stage_ms}")
-for slab in (0, 256, 0, 256):
-    if slab: os.environ["KAPTIVE_B200_SLAB"] = str(slab)
-    else: os.environ["KAPTIVE_B200_SLAB"] = "100000"
+for slab in [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,256,0,256".split(","))]:
+    os.environ["KAPTIVE_B200_SLAB"] = str(abs(slab)) if slab else "100000"
+    os.environ["KAPTIVE_B200_SLAB_THREADS"] = "3" if slab < 0 else "2"  # negative: three host threads
     cap = 1024 * n
     h, arrays = mapper.alloc_hits(cap); cig = np.zeros(cap * 16, dtype=np.uint32)
-    for rep in range(6):
+    for rep in range(5):
         nh, ncg = C.c_int64(0), C.c_int64(0)
         t0 = time.perf_counter()
         check(L.kb_map_assemblies(gi._h, C.c_void_p(host.data_ptr()), ptr(off), ptr(ln), ptr(acs), n, C.byref(h), C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
