@@ -87,6 +87,26 @@ def test_scan_minimizers_equal_sequential_sketch(env):
     assert sorted(zip(h.tolist(), c.tolist(), p.tolist())) == sorted(want)
 
 
+def test_scan_minimizers_adversarial_sequences(env):
+    """Tandem repeats, two-letter sequence, inverted repeats, N runs, contigs around the w + k thresholds and across chunk
+    boundaries: the position-parallel sketch must emit mm_sketch's multiset, identical-k-mer rules included."""
+    sys.path.insert(0, str(ROOT / "scripts"))
+    from proto_sketch_parallel import rand_seq
+
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 14, 15, 23, 24, 25, 26, 31, 32, 33, 40, 63, 64, 65, 100, 300, 700, 8191, 8192, 8193, 8215, 8217, 20000, 70000]
+    contigs = [rand_seq(rng, n, t % 5) for t, n in enumerate(lens * 3)]
+    contigs += [b"A" * 9000, b"AC" * 4600, (b"ACGTTGCA" * 40 + b"N") * 30, b"N" * 50 + rand_seq(rng, 500, 0) + b"N" * 50]
+    b = env["mapper"].AssemblyBatch.from_contigs([[c for c in contigs if len(c)]])
+    h, c, p = env["gi"].scan_minimizers(b, 0, 2_000_000)
+    want = []
+    for ci, s in enumerate(c for c in contigs if len(c)):
+        x, y = ol.sketch(s)
+        want += [(int(a >> 8), ci, int(bb)) for a, bb in zip(x, y)]
+    assert len(h) == len(want)
+    assert sorted(zip(h.tolist(), c.tolist(), p.tolist())) == sorted(want)
+
+
 def test_host_buffer_entry_point_equals_batch_path(env):
     from kaptive_b200 import _lib
 
