@@ -67,13 +67,11 @@ struct ScanRing {
     uint32_t x[64], y[64], a2x[64], a2y[64], a4x[64], a4y[64], mx[64], my[64];  // [tile parity][lane]
 };
 
-// (ax, ay): later entries, (bx, by): earlier ones -> the minimum, the later one among equals
-__device__ __forceinline__ void kb_ladder(uint32_t &ax, uint32_t &ay, uint32_t bx, uint32_t by, bool &tie)
-{
-    tie |= ax == bx;
-    ay = ax <= bx ? ay : by;
-    ax = min(ax, bx);
-}
+// Ring accesses by 32-bit shared address + immediate offset: the six lane addresses below are computed once per kernel
+// (the compiler would otherwise rebuild them from the thread index in every tile, a sixth of the loop's instructions).
+#define KB_LDS(dst, addr, off) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dst) : "r"((addr) + (uint32_t)(off)) : "memory")
+#define KB_STS(addr, off, v) asm volatile("st.shared.u32 [%0], %1;" ::"r"((addr) + (uint32_t)(off)), "r"(v) : "memory")
+enum { RX = 0, RY = 256, RA2X = 512, RA2Y = 768, RA4X = 1024, RA4Y = 1280, RMX = 1536, RMY = 1792 };  // byte offsets in ScanRing
 
 template <int W, int K>
 __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
@@ -95,13 +93,23 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
     unsigned n_emit = 0;                       // this lane's regular emissions (all of them, whatever the presence filter says)
     const bool nofilter = mz_hash != nullptr;  // minimizer dump (parity tests): every minimizer has to reach the queue
     const uint32_t mask = (1u << (2 * K)) - 1u;
-    // ring slots of the entry d positions back, for even and odd tiles
-    int s0[2], s1[2], s2[2], s4[2], s8[2], s10[2];
-#pragma unroll
-    for (int par = 0; par < 2; ++par) {
-        const int b = par * 32 + lane;
-        s0[par] = b, s1[par] = (b - 1) & 63, s2[par] = (b - 2) & 63, s4[par] = (b - 4) & 63, s8[par] = (b - 8) & 63, s10[par] = (b - 10) & 63;
+    // shared addresses of the lane's ring slot in an even tile (a0) and of the slots d positions back from it (wrapping
+    // into the odd half); in an odd tile the slot is a0 + 128 and the slots behind it are plain negative offsets
+    uint32_t a0, w1, w2, w4, w8, w10;
+    {
+        const uint32_t rb = (uint32_t)__cvta_generic_to_shared(&R);
+        a0 = rb + 4u * (uint32_t)lane;
+        w1 = rb + 4u * (uint32_t)((lane - 1) & 63), w2 = rb + 4u * (uint32_t)((lane - 2) & 63), w4 = rb + 4u * (uint32_t)((lane - 4) & 63);
+        w8 = rb + 4u * (uint32_t)((lane - 8) & 63), w10 = rb + 4u * (uint32_t)((lane - 10) & 63);
+        asm volatile("" : "+r"(a0), "+r"(w1), "+r"(w2), "+r"(w4), "+r"(w8), "+r"(w10));
     }
+#define KB_BACK(dst, D, WD, OFF)                                   \
+    do {                                                           \
+        if (PAR == 0) KB_LDS(dst, WD, OFF);                        \
+        else KB_LDS(dst, a0, (OFF) + 128 - 4 * (D));               \
+    } while (0)
+    const uint32_t *const bloom = ix.bloom;
+    const uint32_t bloom_mask = ix.bloom_mask;
     // the lane's k-mer window [i-14, i] inside (previous word : tile low word : tile high word)
     const bool sel_a = lane < 14, sel_c = lane >= 30;
     const int ksh = 2 * ((lane + 2) & 15);
@@ -127,14 +135,16 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             if (front + k < KB_QCAP - 96) Q.x[KB_QCAP - 1 - k] = x, Q.y[KB_QCAP - 1 - k] = y;
             else atomicOr(&counters[6], 1ull);
         };
-        // one silent tile in front of every chunk but the first rebuilds the window state (w + k - 1 = 24 < 32 bases)
-        const int n_sil = cstart > 0 ? 1 : 0;
+        // two silent tiles in front of every chunk but the first rebuild the window state (w + k - 1 = 24 bases are needed;
+        // 64 keep the pair loads below 16-byte aligned)
+        const int n_sil = cstart > 0 ? 2 : 0;
         const int n_tiles = n_sil + ((cend - cstart + 31) >> 5);
         int pos = cstart - 32 * n_sil;  // contig position of lane 0 of the current tile
         const uint32_t *gw = bt.seq2 + ((soff + pos) >> 4);
         const uint32_t *gm = bt.nmask + ((soff + pos) >> 5);
         uint32_t wprev = __ldg(gw - 1), mprev = __ldg(gm - 1);
-        uint32_t wlo = __ldg(gw), whi = __ldg(gw + 1), mcur = __ldg(gm);
+        uint4 sq = __ldg(reinterpret_cast<const uint4 *>(gw));  // sequence and mask words of the current pair of tiles
+        uint2 mk = __ldg(reinterpret_cast<const uint2 *>(gm));
         bool pe = false;  // deferred emission: valid, hash, position, bitmap word
         uint32_t px = 0, py = 0, pw = 0;
         uint32_t lmx = KB_MAXU, lmy = KB_MAXU;  // M[i] of the last tile
@@ -147,37 +157,57 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             }
             front += __popc(bal);
         };
-        auto tile = [&](const int par, const bool live) {
+        auto tile = [&](const int PAR, const bool live, const uint32_t wp, const uint32_t wlo, const uint32_t whi, const uint32_t mp,
+                        const uint32_t mcur) {
+            const uint32_t ao = a0 + PAR * 128;  // folded into the address immediates
             const int i = pos + lane;
-            const uint32_t lo = sel_a ? wprev : (sel_c ? whi : wlo), hi = sel_a ? wlo : (sel_c ? 0u : whi);
+            const uint32_t lo = sel_a ? wp : (sel_c ? whi : wlo), hi = sel_a ? wlo : (sel_c ? 0u : whi);
             const uint32_t win = __funnelshift_r(lo, hi, ksh) & mask;  // base i-14 in bits 0-1 ... base i in bits 28-29
             uint32_t t = __brev(win);
             t = ((t >> 1) & 0x55555555u) | ((t & 0x55555555u) << 1);
             const uint32_t fwd = t >> 2, rev = ~win & mask;
             const uint32_t z = fwd < rev ? 0u : 1u;
-            const int l = __clz((int)__funnelshift_l(pos == 0 ? 0xffffffffu : mprev, mcur, 31 - lane));  // unambiguous run ending at i (<= 32)
-            uint32_t x = KB_MAXU, y = KB_MAXU;
-            if (l >= K) x = kb_hash32(z ? rev : fwd, mask), y = ((uint32_t)i << 1) | z;
-            R.x[s0[par]] = x, R.y[s0[par]] = y;
-            wprev = whi, mprev = mcur;
-            gw += 2, gm += 1, pos += 32;
-            wlo = __ldg(gw), whi = __ldg(gw + 1), mcur = __ldg(gm);  // next tile (the storage is padded by 128 bases)
+            const int l = __clz((int)__funnelshift_l(pos == 0 ? 0xffffffffu : mp, mcur, 31 - lane));  // unambiguous run ending at i (<= 32)
+            const uint32_t h = kb_hash32(min(fwd, rev), mask);
+            const uint32_t x = l >= K ? h : KB_MAXU, y = l >= K ? (((uint32_t)i << 1) | z) : KB_MAXU;
+            KB_STS(ao, RX, x);
+            KB_STS(ao, RY, y);
+            pos += 32;
             __syncwarp();
-            bool tie = false;
-            uint32_t ax = x, ay = y;
-            const uint32_t x10 = R.x[s10[par]];
-            kb_ladder(ax, ay, R.x[s1[par]], R.y[s1[par]], tie);
-            R.a2x[s0[par]] = ax, R.a2y[s0[par]] = ay;
+            bool tie;
+            uint32_t ax = x, ay = y, bx, x10;
+            // ladder step: (ax, ay) the later entries, b the earlier ones -> the minimum, the later one among equals
+            KB_BACK(bx, 1, w1, RX);
+            KB_BACK(x10, 10, w10, RX);
+            tie = ax == bx;
+            if (ax > bx) KB_BACK(ay, 1, w1, RY);
+            ax = min(ax, bx);
+            KB_STS(ao, RA2X, ax);
+            KB_STS(ao, RA2Y, ay);
             __syncwarp();
-            const uint32_t cx = R.a2x[s8[par]], cy = R.a2y[s8[par]];
-            kb_ladder(ax, ay, R.a2x[s2[par]], R.a2y[s2[par]], tie);
-            R.a4x[s0[par]] = ax, R.a4y[s0[par]] = ay;
+            uint32_t cx, cy;
+            KB_BACK(bx, 2, w2, RA2X);
+            KB_BACK(cx, 8, w8, RA2X);
+            KB_BACK(cy, 8, w8, RA2Y);
+            tie |= ax == bx;
+            if (ax > bx) KB_BACK(ay, 2, w2, RA2Y);
+            ax = min(ax, bx);
+            KB_STS(ao, RA4X, ax);
+            KB_STS(ao, RA4Y, ay);
             __syncwarp();
-            kb_ladder(ax, ay, R.a4x[s4[par]], R.a4y[s4[par]], tie);
-            kb_ladder(ax, ay, cx, cy, tie);
-            R.mx[s0[par]] = ax, R.my[s0[par]] = ay;
+            KB_BACK(bx, 4, w4, RA4X);
+            tie |= ax == bx;
+            if (ax > bx) KB_BACK(ay, 4, w4, RA4Y);
+            ax = min(ax, bx);
+            tie |= ax == cx;
+            ay = ax > cx ? cy : ay;
+            ax = min(ax, cx);
+            KB_STS(ao, RMX, ax);
+            KB_STS(ao, RMY, ay);
             __syncwarp();
-            const uint32_t omx = R.mx[s1[par]], omy = R.my[s1[par]];
+            uint32_t omx, omy;
+            KB_BACK(omx, 1, w1, RMX);
+            KB_BACK(omy, 1, w1, RMY);
             lmx = ax, lmy = ay;
             const bool act = live && i < cend;
             const bool e2 = x10 < ax && l >= W + K - 1;
@@ -185,14 +215,15 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             n_emit += e ? 1u : 0u;
             const bool anyt = __any_sync(0xffffffffu, tie);
             if (anyt || ptie) {  // equal hashes somewhere near: the identical-k-mer rules of mm_sketch
+                const int own = PAR * 32 + lane;
                 if (act && l == W + K - 1 && omx != KB_MAXU)
                     for (int d = 1; d < W; ++d) {
-                        const uint32_t jx = R.x[(s0[par] - d) & 63], jy = R.y[(s0[par] - d) & 63];
+                        const uint32_t jx = R.x[(own - d) & 63], jy = R.y[(own - d) & 63];
                         if (jx == omx && jy != omy) slow(jx, jy);
                     }
                 if (act && e2 && ax != KB_MAXU)
                     for (int d = 0; d < W; ++d) {
-                        const uint32_t jx = R.x[(s0[par] - d) & 63], jy = R.y[(s0[par] - d) & 63];
+                        const uint32_t jx = R.x[(own - d) & 63], jy = R.y[(own - d) & 63];
                         if (jx == ax && jy != ay) slow(jx, jy);
                     }
                 __syncwarp();
@@ -201,7 +232,7 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             // presence filter, one tile deferred so that the bitmap load (L2) is not waited for
             push(pe && (nofilter || ((pw >> (px & 31u)) & 1u)), px, py);
             pe = e, px = omx, py = omy;
-            if (e && !nofilter) pw = __ldg(ix.bloom + ((omx & ix.bloom_mask) >> 5));
+            if (e && !nofilter) pw = __ldg(bloom + ((omx & bloom_mask) >> 5));
         };
         auto drain = [&]() {
             __syncwarp();
@@ -259,8 +290,12 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             __syncwarp();
         };
         for (int u = 0; u < n_tiles; u += 2) {
-            tile(0, u >= n_sil);
-            if (u + 1 < n_tiles) tile(1, true);
+            gw += 4, gm += 2;
+            const uint4 nsq = __ldg(reinterpret_cast<const uint4 *>(gw));  // next pair (the storage is padded by 128 bases)
+            const uint2 nmk = __ldg(reinterpret_cast<const uint2 *>(gm));
+            tile(0, u >= n_sil, wprev, sq.x, sq.y, mprev, mk.x);
+            if (u + 1 < n_tiles) tile(1, u >= n_sil, sq.y, sq.z, sq.w, mk.x, mk.y);
+            wprev = sq.w, mprev = mk.y, sq = nsq, mk = nmk;
             __syncwarp();
             if (front + tail >= 32) drain();
         }
