@@ -15,6 +15,9 @@
 #include "kb_scan.cuh"
 #include "kb_kernels.h"
 
+#ifndef KB_SCAN_CTAS
+#define KB_SCAN_CTAS 6  // CTAs of 128 threads per SM (measured: 8 CTAs at 64 registers are 5 % slower, the kernel is ALU-pipe bound)
+#endif
 #define KB_QCAP 512  // queue capacity per warp: 31 leftover + two tiles of 32 regular pushes in front, the rare identical-k-mer pushes from the back
 
 // key/val of one anchor: assembly minimizer (rid-local pos `tpos`, strand tz) x gene entry e
@@ -74,7 +77,7 @@ struct ScanRing {
 enum { RX = 0, RY = 256, RA2X = 512, RA2Y = 768, RA4X = 1024, RA4Y = 1280, RMX = 1536, RMY = 1792 };  // byte offsets in ScanRing
 
 template <int W, int K>
-__global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
+__global__ void __launch_bounds__(128, KB_SCAN_CTAS) kb_scan_kernel(KbIndexView ix, KbBatchView bt, uint64_t *akey, uint32_t *aval,
                                                       unsigned long long *counters, int64_t anchor_cap,
                                                       uint32_t *mz_hash, int32_t *mz_ctg, uint32_t *mz_pos,
                                                       int64_t mz_cap, int32_t mz_asm)
@@ -108,12 +111,17 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
         if (PAR == 0) KB_LDS(dst, WD, OFF);                        \
         else KB_LDS(dst, a0, (OFF) + 128 - 4 * (D));               \
     } while (0)
-    const uint32_t *const bloom = ix.bloom;
-    const uint32_t bloom_mask = ix.bloom_mask;
-    // the lane's k-mer window [i-14, i] inside (previous word : tile low word : tile high word)
-    const bool sel_a = lane < 14, sel_c = lane >= 30;
-    const int ksh = 2 * ((lane + 2) & 15);
-
+    // loop invariants the compiler would otherwise re-read from the parameter bank (or rebuild from the thread index) per tile
+    const uint32_t *bloom = ix.bloom;
+    uint32_t bloom_mask = ix.bloom_mask;
+    uint32_t nf_mask = nofilter ? 0xffffffffu : 0u;  // ORed into the bitmap word: the dump sees every minimizer
+    uint32_t qb = (uint32_t)__cvta_generic_to_shared(&Q);
+    asm volatile("" : "+l"(bloom), "+r"(bloom_mask), "+r"(nf_mask), "+r"(qb));
+    // the lane's k-mer window [i-14, i] starts (lane + 2) bases into the word in front of the tile: the lane reads the two
+    // words that hold it itself (through L1; the warp touches three consecutive words) and funnel-shifts them
+    const int kword = ((lane + 2) >> 4) - 1;
+    uint32_t ksh = 2 * ((lane + 2) & 15), msh = 31 - lane;
+    asm volatile("" : "+r"(ksh), "+r"(msh));
     for (int64_t chunk = (int64_t)blockIdx.x * 4 + warp; chunk < bt.n_chunks; chunk += n_warps) {
         const int ctg = bt.chunk_ctg[chunk];
         const int cstart = bt.chunk_start[chunk];
@@ -142,9 +150,10 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
         int pos = cstart - 32 * n_sil;  // contig position of lane 0 of the current tile
         const uint32_t *gw = bt.seq2 + ((soff + pos) >> 4);
         const uint32_t *gm = bt.nmask + ((soff + pos) >> 5);
-        uint32_t wprev = __ldg(gw - 1), mprev = __ldg(gm - 1);
-        uint4 sq = __ldg(reinterpret_cast<const uint4 *>(gw));  // sequence and mask words of the current pair of tiles
-        uint2 mk = __ldg(reinterpret_cast<const uint2 *>(gm));
+        gw += kword;  // per lane from here on
+        uint32_t mprev = __ldg(gm - 1);
+        uint32_t k0 = __ldg(gw), k1 = __ldg(gw + 1);             // the lane's sequence words of the current tile
+        uint2 mk = __ldg(reinterpret_cast<const uint2 *>(gm));  // mask words of the current pair of tiles
         bool pe = false;  // deferred emission: valid, hash, position, bitmap word
         uint32_t px = 0, py = 0, pw = 0;
         uint32_t lmx = KB_MAXU, lmy = KB_MAXU;  // M[i] of the last tile
@@ -152,22 +161,23 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
         auto push = [&](bool pass, uint32_t x, uint32_t y) {
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
             if (pass) {
-                const int o = front + __popc(bal & ((1u << lane) - 1u));
-                Q.x[o] = x, Q.y[o] = y;
+                const uint32_t o = qb + 4u * (uint32_t)(front + __popc(bal & ((1u << lane) - 1u)));
+                KB_STS(o, 0, x);
+                KB_STS(o, 4 * KB_QCAP, y);
             }
             front += __popc(bal);
         };
-        auto tile = [&](const int PAR, const bool live, const uint32_t wp, const uint32_t wlo, const uint32_t whi, const uint32_t mp,
-                        const uint32_t mcur) {
+        auto tile = [&](const int PAR, const bool live, const uint32_t mp, const uint32_t mcur) {
             const uint32_t ao = a0 + PAR * 128;  // folded into the address immediates
             const int i = pos + lane;
-            const uint32_t lo = sel_a ? wp : (sel_c ? whi : wlo), hi = sel_a ? wlo : (sel_c ? 0u : whi);
-            const uint32_t win = __funnelshift_r(lo, hi, ksh) & mask;  // base i-14 in bits 0-1 ... base i in bits 28-29
+            const uint32_t win = __funnelshift_r(k0, k1, ksh) & mask;  // base i-14 in bits 0-1 ... base i in bits 28-29
+            gw += 2;
+            k0 = __ldg(gw), k1 = __ldg(gw + 1);  // next tile (the storage is padded by 128 bases)
             uint32_t t = __brev(win);
             t = ((t >> 1) & 0x55555555u) | ((t & 0x55555555u) << 1);
             const uint32_t fwd = t >> 2, rev = ~win & mask;
             const uint32_t z = fwd < rev ? 0u : 1u;
-            const int l = __clz((int)__funnelshift_l(pos == 0 ? 0xffffffffu : mp, mcur, 31 - lane));  // unambiguous run ending at i (<= 32)
+            const int l = __clz((int)__funnelshift_l(PAR == 0 && pos == 0 ? 0xffffffffu : mp, mcur, msh));  // unambiguous run ending at i (<= 32)
             const uint32_t h = kb_hash32(min(fwd, rev), mask);
             const uint32_t x = l >= K ? h : KB_MAXU, y = l >= K ? (((uint32_t)i << 1) | z) : KB_MAXU;
             KB_STS(ao, RX, x);
@@ -211,7 +221,8 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             lmx = ax, lmy = ay;
             const bool act = live && i < cend;
             const bool e2 = x10 < ax && l >= W + K - 1;
-            const bool e = act && (e2 || (x <= omx && l >= W + K && omx != KB_MAXU));
+            // E1 needs omx != MAX: as signed numbers MAX is -1 and a valid x (l >= k) is never below it
+            const bool e = act && (e2 || ((int32_t)x <= (int32_t)omx && l >= W + K));
             n_emit += e ? 1u : 0u;
             const bool anyt = __any_sync(0xffffffffu, tie);
             if (anyt || ptie) {  // equal hashes somewhere near: the identical-k-mer rules of mm_sketch
@@ -230,9 +241,9 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             }
             ptie = anyt;
             // presence filter, one tile deferred so that the bitmap load (L2) is not waited for
-            push(pe && (nofilter || ((pw >> (px & 31u)) & 1u)), px, py);
+            push(pe && ((pw >> (px & 31u)) & 1u), px, py);
             pe = e, px = omx, py = omy;
-            if (e && !nofilter) pw = __ldg(bloom + ((omx & bloom_mask) >> 5));
+            if (e) pw = __ldg(bloom + ((omx & bloom_mask) >> 5)) | nf_mask;
         };
         auto drain = [&]() {
             __syncwarp();
@@ -290,16 +301,15 @@ __global__ void __launch_bounds__(128, 6) kb_scan_kernel(KbIndexView ix, KbBatch
             __syncwarp();
         };
         for (int u = 0; u < n_tiles; u += 2) {
-            gw += 4, gm += 2;
-            const uint4 nsq = __ldg(reinterpret_cast<const uint4 *>(gw));  // next pair (the storage is padded by 128 bases)
-            const uint2 nmk = __ldg(reinterpret_cast<const uint2 *>(gm));
-            tile(0, u >= n_sil, wprev, sq.x, sq.y, mprev, mk.x);
-            if (u + 1 < n_tiles) tile(1, u >= n_sil, sq.y, sq.z, sq.w, mk.x, mk.y);
-            wprev = sq.w, mprev = mk.y, sq = nsq, mk = nmk;
+            gm += 2;
+            const uint2 nmk = __ldg(reinterpret_cast<const uint2 *>(gm));  // next pair
+            tile(0, u >= n_sil, mprev, mk.x);
+            if (u + 1 < n_tiles) tile(1, u >= n_sil, mk.x, mk.y);
+            mprev = mk.y, mk = nmk;
             __syncwarp();
             if (front + tail >= 32) drain();
         }
-        push(pe && (nofilter || ((pw >> (px & 31u)) & 1u)), px, py);  // the deferred emission of the last tile
+        push(pe && ((pw >> (px & 31u)) & 1u), px, py);  // the deferred emission of the last tile
         {  // mm_sketch's final push, by the lane that holds the last base of the contig
             const bool e = cend == clen && clen > 0 && lane == ((clen - 1) & 31) && lmx != KB_MAXU;
             push(e, lmx, lmy);
@@ -323,7 +333,7 @@ void kb_launch_scan(const KbIndexView &ix, const KbBatchView &bt, uint64_t *akey
 {
     if (bt.n_chunks == 0) return;
     int64_t want = (bt.n_chunks + 3) / 4;
-    int64_t grid = (int64_t)n_sm * 6;  // 6 CTAs of 128 threads (24 KB of shared memory each) per SM, grid-stride over the chunks
+    int64_t grid = (int64_t)n_sm * KB_SCAN_CTAS;  // grid-stride over the chunks
     if (grid > want) grid = want;
     cudaFuncSetAttribute(kb_scan_kernel<10, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanQueue)));  // per device
     kb_scan_kernel<10, 15><<<(unsigned)grid, 128, 4 * sizeof(ScanQueue), st>>>(ix, bt, akey, aval, counters, anchor_cap, mz_hash, mz_ctg,
