@@ -6,6 +6,9 @@
 // of the last w window entries and of l = min(run of unambiguous bases, w+k),
 // so a lane that starts KB_SCAN_LOOKBACK = w+k-1 bases early in "silent" mode
 // reproduces the sequential state bit for bit ("Scan kernel").
+// Used on the host: the gene sketch at index build (kb_index.cpp) and the host
+// emulation of the pipeline (tests/host_emul).  The assembly scan on the GPU
+// (kb_scan.cu) evaluates a position-parallel restatement of the same rules.
 //
 // K must be odd (a k-mer can then never equal its reverse complement, which
 // removes mm_sketch's `continue` that stalls the window); K <= 15 keeps the
