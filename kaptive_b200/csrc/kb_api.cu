@@ -901,17 +901,34 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
 {
     if (!ix) return fail(KB_ERR_ARG, "null index");
     if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
-    int slab = 768, n_slabs;
-    if (const char *e = getenv("KAPTIVE_B200_SLAB")) {  // explicit slab size: cut whenever the call is larger
-        slab = atoi(e) > 0 ? atoi(e) : slab;
-        n_slabs = n_asm <= slab ? 1 : (n_asm + slab - 1) / slab;
-    } else n_slabs = n_asm < 512 ? 1 : std::max(2, (n_asm + slab - 1) / slab);
-    if (n_slabs > 1) slab = (n_asm + n_slabs - 1) / n_slabs;  // equal slabs
+    // slab boundaries (assembly indices): bnd[k] .. bnd[k+1]
+    std::vector<int> bnd{0};
+    if (const char *e = getenv("KAPTIVE_B200_SLAB_PLAN")) {  // experiments: explicit slab sizes, e.g. "150,425,425" (the last one repeats)
+        int last = 0;
+        for (const char *q = e; bnd.back() < n_asm;) {
+            int v = atoi(q);
+            if (v > 0) last = v;
+            if (last <= 0) break;
+            bnd.push_back(std::min(n_asm, bnd.back() + last));
+            const char *c = strchr(q, ',');
+            q = c ? c + 1 : "";
+        }
+    } else {
+        int slab = 768, n;
+        if (const char *e = getenv("KAPTIVE_B200_SLAB")) {  // explicit slab size: cut whenever the call is larger
+            slab = atoi(e) > 0 ? atoi(e) : slab;
+            n = n_asm <= slab ? 1 : (n_asm + slab - 1) / slab;
+        } else n = n_asm < 512 ? 1 : std::max(2, (n_asm + slab - 1) / slab);
+        const int each = n > 1 ? (n_asm + n - 1) / n : n_asm;  // equal slabs
+        for (int k = 1; k <= n; ++k) bnd.push_back(std::min(n_asm, k * each));
+    }
+    if (bnd.back() < n_asm || bnd.size() < 2) bnd.assign({0, n_asm});
+    const int n_slabs = (int)bnd.size() - 1;
     std::vector<kb_result_t *> res((size_t)n_slabs, nullptr);
     std::vector<int> rcs((size_t)n_slabs, KB_OK);
     std::vector<std::string> errs((size_t)n_slabs);
     auto run_slab = [&](int k) {
-        const int a0 = n_slabs == 1 ? 0 : k * slab, a1 = n_slabs == 1 ? n_asm : std::min(n_asm, a0 + slab);
+        const int a0 = bnd[(size_t)k], a1 = bnd[(size_t)k + 1];
         const int c0 = asm_contig_start[a0];
         std::vector<int32_t> acs((size_t)(a1 - a0) + 1);
         for (int a = a0; a <= a1; ++a) acs[(size_t)(a - a0)] = asm_contig_start[a] - c0;
@@ -956,7 +973,7 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
             OFF(matches); OFF(block_len); OFF(edit_distance); OFF(mapq); OFF(is_primary); OFF(cigar_off); OFF(n_cigar);
 #undef OFF
             rc = kb_result_fetch(r, &v, cigar ? cigar + oc : nullptr, cigar_cap - oc);
-            const int a0 = n_slabs == 1 ? 0 : k * slab;
+            const int a0 = bnd[(size_t)k];
             if (!rc && (a0 || oc))
                 for (int64_t i = 0; i < r->n_hits; ++i) {
                     if (v.asm_id) v.asm_id[i] += a0;

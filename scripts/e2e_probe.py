@@ -20,14 +20,18 @@ for rep in range(4):
     r = gi.map(b, fetch=True)
     t2 = time.perf_counter()
     print(f"n={n} batch_create {1e3*(t1-t0):.1f} ms ({n*5e6/(t1-t0)/1e9:.1f} GB/s)  map+fetch {1e3*(t2-t1):.1f} ms  stages {r.stage_ms}")
-for slab in [int(v) for v in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0,256,0,256".split(","))]:
-    os.environ["KAPTIVE_B200_SLAB"] = str(abs(slab)) if slab else "100000"
-    os.environ["KAPTIVE_B200_SLAB_THREADS"] = "3" if slab < 0 else "2"  # negative: three host threads
+plans = sys.argv[2].split("/") if len(sys.argv) > 2 else ["500", "150,425", "500", "150,425"]
+for plan in plans:  # slab plans "a,b,c" (the last size repeats); a leading "t3:" uses three host threads
+    thr = "2"
+    if plan.startswith("t3:"): thr, plan = "3", plan[3:]
+    os.environ["KAPTIVE_B200_SLAB_PLAN"] = plan
+    os.environ["KAPTIVE_B200_SLAB_THREADS"] = thr
     cap = 1024 * n
     h, arrays = mapper.alloc_hits(cap); cig = np.zeros(cap * 16, dtype=np.uint32)
-    for rep in range(5):
+    ts = []
+    for rep in range(6):
         nh, ncg = C.c_int64(0), C.c_int64(0)
         t0 = time.perf_counter()
         check(L.kb_map_assemblies(gi._h, C.c_void_p(host.data_ptr()), ptr(off), ptr(ln), ptr(acs), n, C.byref(h), C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
-        t1 = time.perf_counter()
-        print(f"slab={slab} kb_map_assemblies {1e3*(t1-t0):.1f} ms -> {n/(t1-t0):.0f} asm/s hits {nh.value}")
+        ts.append(1e3 * (time.perf_counter() - t0))
+    print(f"plan={plan} threads={thr}: " + " ".join(f"{t:.0f}" for t in ts) + f" ms; best {n / min(ts) * 1e3:.0f} asm/s, median {n / sorted(ts)[len(ts) // 2] * 1e3:.0f} asm/s, hits {nh.value}")
