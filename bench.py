@@ -254,8 +254,11 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # host arrays of the resident step, reused from step to step like a production caller would
+    out_h, out_arrays = mapper.alloc_hits(1024 * a.n_asm)
+    out = (out_h, out_arrays, np.zeros(1024 * a.n_asm * 16, dtype=np.uint32))
     for _ in range(a.warmup):
-        gi.map(batch, fetch=True)
+        gi.map(batch, fetch=True, out=out)
     barrier()
     dp_raw = np.zeros(32, dtype=np.int64)
     L.kb_debug_dp_stats(None, 1)
@@ -267,7 +270,7 @@ def run_ours(a):
     n_hits = 0
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        res = gi.map(batch, fetch=True)
+        res = gi.map(batch, fetch=True, out=out)
         n_hits = len(res)
         counters = res.counters
         for k, v in res.stage_ms.items():
@@ -333,7 +336,11 @@ def run_ours(a):
     dominant = {"kernels": "kb_rows_kernel + kb_band_kernel (base-level DP)", "share_of_step": align_ms / dev_ms if dev_ms else None,
                 "dp_cells_per_step": int(counters.get("dp_cells", 0)),
                 "gcups": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 if align_ms else None,
-                "bound": "integer issue (ALU pipe), not HBM: 1 B of traceback per cell"}
+                "bound": "integer issue (ALU pipe), not HBM: 1 B of traceback per cell",
+                # the same kernels against the HBM roofline: algorithmic bytes = 1 B of traceback written per DP cell
+                "hbm": {"achieved": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 if align_ms else None, "peak": peak, "unit": "GB/s",
+                        "frac": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 / peak if align_ms and peak else None,
+                        "traffic": "ncu: 127 GB written per 1000 assemblies (profiles/ncu_r1_final_details.csv: 24.9 + 7.1 GB per 250)"}}
 
     cpu = None
     if not a.no_cpu_baseline:

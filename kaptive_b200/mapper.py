@@ -144,12 +144,15 @@ class GeneIndex:
         check(L.kb_index_deserialize(ptr(buf), len(buf), device, C.byref(h)))
         return cls(device=device, _handle=h)
 
-    def map(self, batch: AssemblyBatch, fetch: bool = True) -> MapResult:
+    def map(self, batch: AssemblyBatch, fetch: bool = True, out=None) -> MapResult:
+        """Map every gene onto every assembly of `batch`.  `out` = (KbHits, arrays, cigar) from `alloc_hits` plus a uint32
+        cigar pool lets a caller that maps batch after batch reuse its host arrays (a fresh 30 MB of numpy arrays per call
+        costs more in page faults than the copy itself); the result's arrays are then views of them."""
         L = _lib.load()
         r = C.c_void_p(0)
         check(L.kb_map_batch(self._h, batch._h, C.byref(r)))
         try:
-            return _drain(L, r, batch.n_asm, fetch)
+            return _drain(L, r, batch.n_asm, fetch, out)
         finally:
             L.kb_result_destroy(r)
 
@@ -196,7 +199,7 @@ def alloc_hits(n: int) -> tuple[KbHits, dict[str, np.ndarray]]:
     return h, arrays
 
 
-def _drain(L, r, n_asm: int, fetch: bool) -> MapResult:
+def _drain(L, r, n_asm: int, fetch: bool, out=None) -> MapResult:
     nh, nc = C.c_int64(0), C.c_int64(0)
     check(L.kb_result_size(r, C.byref(nh), C.byref(nc)))
     ms = np.zeros(KB_N_STAGES, dtype=np.float32)
@@ -208,8 +211,11 @@ def _drain(L, r, n_asm: int, fetch: bool) -> MapResult:
     hits: dict[str, np.ndarray] = {name: np.zeros(0, dtype=dt) for name, dt in HIT_FIELDS}
     cigar = np.zeros(0, dtype=np.uint32)
     if fetch:
-        h, arrays = alloc_hits(nh.value)
-        cigar = np.zeros(max(nc.value, 1), dtype=np.uint32)
+        if out is not None:
+            h, arrays, cigar = out  # too small: kb_result_fetch reports KB_ERR_CAPACITY
+        else:
+            h, arrays = alloc_hits(nh.value)
+            cigar = np.zeros(max(nc.value, 1), dtype=np.uint32)
         check(L.kb_result_fetch(r, C.byref(h), ptr(cigar), len(cigar)))
         hits = {k: v[: nh.value] for k, v in arrays.items()}
         cigar = cigar[: nc.value]

@@ -75,6 +75,21 @@ def test_batch_composition_does_not_change_results(env):
         check_against(r1, 0, GOLD[f"{name}/hits"], GOLD[f"{name}/cigar"])
 
 
+def test_map_into_caller_arrays_equals_fresh_arrays(env):
+    contigs = env["built"]["mutated1"][1]
+    b = env["mapper"].AssemblyBatch.from_contigs([[s for _, s in contigs]])
+    h, arrays = env["mapper"].alloc_hits(4096)
+    out = (h, arrays, np.zeros(1 << 16, dtype=np.uint32))
+    r0, r1 = env["gi"].map(b), env["gi"].map(b, out=out)
+    assert len(r0) == len(r1) > 0
+    for k in r0.hits:
+        assert np.array_equal(r0.hits[k], r1.hits[k]), k
+    assert np.array_equal(r0.cigar, r1.cigar)
+    tiny = (env["mapper"].alloc_hits(1)[0], {}, np.zeros(1, dtype=np.uint32))
+    with pytest.raises(Exception):
+        env["gi"].map(b, out=tiny)
+
+
 def test_scan_minimizers_equal_sequential_sketch(env):
     name = "boundaries"
     contigs = env["built"][name][1]
