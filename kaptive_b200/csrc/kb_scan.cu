@@ -241,9 +241,9 @@ __global__ void __launch_bounds__(128, KB_SCAN_CTAS) kb_scan_kernel(KbIndexView 
             }
             ptie = anyt;
             // presence filter, one tile deferred so that the bitmap load (L2) is not waited for
-            push(pe && ((pw >> (px & 31u)) & 1u), px, py);
+            push(pe && (((pw | nf_mask) >> (px & 31u)) & 1u), px, py);
             pe = e, px = omx, py = omy;
-            if (e) pw = __ldg(bloom + ((omx & bloom_mask) >> 5)) | nf_mask;
+            if (e) pw = __ldg(bloom + ((omx & bloom_mask) >> 5));  // consumed in the next tile: nothing may touch pw before
         };
         auto drain = [&]() {
             __syncwarp();
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128, KB_SCAN_CTAS) kb_scan_kernel(KbIndexView 
             __syncwarp();
             if (front + tail >= 32) drain();
         }
-        push(pe && ((pw >> (px & 31u)) & 1u), px, py);  // the deferred emission of the last tile
+        push(pe && (((pw | nf_mask) >> (px & 31u)) & 1u), px, py);  // the deferred emission of the last tile
         {  // mm_sketch's final push, by the lane that holds the last base of the contig
             const bool e = cend == clen && clen > 0 && lane == ((clen - 1) & 31) && lmx != KB_MAXU;
             push(e, lmx, lmy);
