@@ -261,10 +261,19 @@ void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChain
 #define KB_SC_QBAND 32
 #define KB_SC_QROWS 33
 
+// The rows kernel's queue has two ends: rectangles of at least big_thr cells are stored from the back of the list and taken
+// first (longest jobs first keeps the tail of the persistent kernel short), the others from the front in planning order.
+#define KB_SC_ROWS_BIG 34
+__device__ __forceinline__ void kb_rows_enqueue(int32_t *rows_list, int64_t job_cap, unsigned long long *counters, int64_t big_thr, const KbJob &J,
+                                                int32_t jid)
+{
+    if (big_thr > 0 && (int64_t)J.qlen * J.tlen >= big_thr) rows_list[job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_ROWS_BIG], 1ull)] = jid;
+    else rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
+}
 __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
                                                       const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, int32_t *kscratch,
                                                       KbPlan *plans, KbJob *jobs, int64_t job_cap, int32_t *band_list, int32_t *rows_list,
-                                                      int32_t *slow_list, unsigned long long *counters)
+                                                      int32_t *slow_list, unsigned long long *counters, int64_t big_thr)
 {
     const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_chains) return;
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchVie
         const KbJob &J = jobs[base + k];
         const bool band = J.kind == KB_JOB_FILL && J.qlen + J.tlen <= 8184 && kb_band_eligible(ix.p.max_sw_cells, J.qlen, J.tlen, J.w, J.flag);
         if (band) band_list[atomicAdd(&counters[KB_SC_BAND], 1ull)] = (int32_t)(base + k);
-        else rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = (int32_t)(base + k);
+        else kb_rows_enqueue(rows_list, job_cap, counters, big_thr, J, (int32_t)(base + k));
     }
 }
 
@@ -325,7 +334,7 @@ static __device__ __forceinline__ void kb_job_finish(int lane, KbJob *J, const K
 #endif
 __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, int32_t *rows_list,
                                                         uint8_t *scratch, size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
-                                                        unsigned long long *counters)
+                                                        unsigned long long *counters, int64_t big_thr)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView 
             }
         }
         if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
-        else if (lane == 0) rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
+        else if (lane == 0) kb_rows_enqueue(rows_list, jobcig_cap / 16, counters, big_thr, *J, jid);
     }
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
 }
@@ -387,14 +396,15 @@ __global__ void __launch_bounds__(128, KB_ROWS_MINB) kb_rows_kernel(KbIndexView 
     for (int x = lane; x < KB_RING_WORDS; x += 32) S.wmax[x] = 0;
     __syncwarp();
     const KbDpConst P = kb_dp_const(ix.p);
-    const long long n = (long long)counters[KB_SC_ROWS];
+    const long long n_big = (long long)counters[KB_SC_ROWS_BIG], n = (long long)counters[KB_SC_ROWS] + n_big;
+    const int64_t job_cap = jobcig_cap / 16;
     int64_t cells = 0;
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(&counters[KB_SC_QROWS], 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
         if ((long long)k >= n) break;
-        KbJob *J = jobs + rows_list[k];
+        KbJob *J = jobs + ((long long)k < n_big ? rows_list[job_cap - 1 - (long long)k] : rows_list[(long long)k - n_big]);
         const int dir = J->kind == KB_JOB_LEFT ? -1 : 1;
         const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff + (dir < 0 ? -1 : 0), dir};
         const KbDirPack st{bt.seq2, bt.nmask, J->tpos + (dir < 0 ? -1 : 0), dir};
@@ -458,20 +468,27 @@ size_t kb_band_scratch_bytes() { return (size_t)KB_CIG_MAX * 4 + 4 * 32 * 8200 +
 size_t kb_sizeof_job() { return sizeof(KbJob); }
 size_t kb_sizeof_plan() { return sizeof(KbPlan); }
 
+static int64_t kb_rows_big_thr()
+{
+    // measured on the bench workload: 255.6 ms (off) -> 251.9 ms (150 k cells) -> 252.3 ms (300 k cells) for the align stage
+    static const int64_t v = getenv("KAPTIVE_B200_ROWS_BIG") ? atoll(getenv("KAPTIVE_B200_ROWS_BIG")) : 150000;
+    return v;
+}
 void kb_launch_stage_plan(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
                           const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, int64_t job_cap, int32_t *band_list,
                           int32_t *rows_list, int32_t *slow_list, unsigned long long *counters, cudaStream_t st)
 {
     if (n_chains <= 0) return;
     kb_plan_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, kscratch, (KbPlan *)plans,
-                                                                       (KbJob *)jobs, job_cap, band_list, rows_list, slow_list, counters);
+                                                                       (KbJob *)jobs, job_cap, band_list, rows_list, slow_list, counters,
+                                                                       kb_rows_big_thr());
 }
 void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, uint8_t *band_scratch,
                         int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
                         unsigned long long *counters, cudaStream_t st)
 {
     kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, rows_list, band_scratch, kb_band_scratch_bytes(),
-                                                               jobcig, jobcig_cap, counters);
+                                                               jobcig, jobcig_cap, counters, kb_rows_big_thr());
     kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, rows_list, rows_scratch, rows_scratch_bytes, jobcig,
                                                                jobcig_cap, counters);
 }
