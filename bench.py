@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""bench.py -- assemblies/s typed against a kpsc_k-shaped gene database (BASELINE.json metric).
+"""bench.py -- assemblies/s against a kpsc_k + kpsc_o shaped gene database in one index (BASELINE.json metric).
 
 A "step" is one pass of the mapping hot path (scan -> sort -> chain -> align -> finalise) over one
-batch of synthetic assemblies.  Default workload = BASELINE.json configs[1]: 1,000 synthetic 5 Mb
-assemblies vs a 150-locus x 20-gene database on one B200.
+batch of synthetic assemblies.  Default workload = BASELINE.json configs[2], the configuration the
+metric is quoted on: 10,000 synthetic 5 Mb assemblies per GPU, every one carrying a K locus and an O
+locus, vs K-shaped 150 x 20 genes + O-shaped 20 x 10 genes + 15 extra genes in ONE index; the batch is
+one resident 18.8 GB packed buffer.  `--db k --n-asm 1000` gives configs[1].
 
   value      : assemblies/s with the 2-bit packed batch already resident in HBM (wall clock between
                device synchronisations, max over ranks; device-event time reported beside it)
@@ -32,8 +34,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-METRIC = "assemblies_per_sec_typed_kpsc_k"
+METRIC = "assemblies_per_sec_mapped_kpsc_k_plus_o"  # overwritten by --db k
 UNIT = "assemblies/s"
+ANCHOR_BYTES = 16  # 16 B per emitted anchor in the scan kernel's algorithmic bytes
 
 
 def parse_args():
@@ -42,20 +45,38 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-asm", type=int, default=1000, help="assemblies per GPU per step")
+    ap.add_argument("--db", default="ko", choices=["ko", "k"], help="ko: K+O combined index (configs[2]); k: K only (configs[1])")
+    ap.add_argument("--n-asm", type=int, default=10000, help="assemblies per GPU per step")
     ap.add_argument("--asm-len", type=int, default=5_000_000)
     ap.add_argument("--n-loci", type=int, default=150)
     ap.add_argument("--genes-per-locus", type=int, default=20)
     ap.add_argument("--n-core", type=int, default=4)
     ap.add_argument("--e2e-asm", type=int, default=1000, help="assemblies per end-to-end step (host buffers)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 2 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 4 x cores, 64..96)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    global METRIC
+    if a.db == "k":
+        METRIC = "assemblies_per_sec_mapped_kpsc_k"
+    return a
 
 
 def workload_name(a) -> str:
-    return (f"{a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU vs kpsc_k-shaped db "
+    if a.db == "ko":
+        return (f"BASELINE configs[2]: {a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU (one resident packed batch), a K and an O "
+                f"locus embedded in each, vs kpsc_k + kpsc_o shaped db in ONE index (K {a.n_loci} loci x {a.genes_per_locus} genes, "
+                f"{a.n_core} core families; O 20 loci x 10 genes, 2 core families, + 15 extra genes)")
+    return (f"BASELINE configs[1]: {a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU vs kpsc_k-shaped db "
             f"({a.n_loci} loci x {a.genes_per_locus} genes, {a.n_core} core families)")
+
+
+def make_db(a):
+    """(database, locus ranges the assemblies draw their embedded loci from)"""
+    from kaptive_b200 import synth
+
+    if a.db == "ko":
+        return synth.make_ko_db(k_loci=a.n_loci, k_genes=a.genes_per_locus, k_core=a.n_core, seed=1)
+    return synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1), None
 
 
 def peaks():
@@ -110,68 +131,132 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def _oracle_worker(args):
-    import oracle_lib as ol  # noqa: E402  (test infrastructure; used here only as the timed CPU baseline)
+_CPU_SAMPLE = None  # (flat_db, [assembly flats]) inherited by the forked workers: no pickling of 5 MB per assembly
 
-    flat_db, asm_flats = args
+
+def _oracle_worker(idx):
+    import oracle_lib as ol  # noqa: E402  (test infrastructure; used here only as the timed CPU baseline / parity checker)
+
+    flat_db, asms = _CPU_SAMPLE
     odb = ol.OracleDB(*flat_db)
-    n = 0
-    for f in asm_flats:
-        n += len(odb.map(*f)["hits"])
-    return n
+    out = []
+    for i in idx:
+        r = odb.map(*asms[i])
+        out.append((i, r["hits"], r["cigar"]))
+    return out
 
 
-def cpu_oracle_rate(db, asms_flat, cores: int) -> tuple[float, float]:
-    """assemblies/s of the oracle over `asms_flat` with one process per core; returns (rate, seconds)."""
+def cpu_oracle_run(db, asms_flat, cores: int):
+    """The oracle over `asms_flat`, one process per core; returns (assemblies/s, seconds, {index: (hits, cigar)})."""
     import multiprocessing as mp
 
-    flat_db = db.flat()
-    shards = [asms_flat[i::cores] for i in range(cores)]
+    global _CPU_SAMPLE
+    _CPU_SAMPLE = (db.flat(), asms_flat)
+    shards = [list(range(i, len(asms_flat), cores)) for i in range(cores)]
     shards = [s for s in shards if s]
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(len(shards)) as pool:
-        pool.map(_oracle_worker, [(flat_db, s) for s in shards])
+        parts = pool.map(_oracle_worker, shards)
     dt = time.perf_counter() - t0
-    return len(asms_flat) / dt, dt
+    res = {i: (h, c) for part in parts for i, h, c in part}
+    return len(asms_flat) / dt, dt, res
 
 
-def host_sample(a, db, n: int):
-    """n assemblies of the workload as host arrays (generated with the same seeded numpy generator family)."""
+def cpu_single_core(db, asms_flat, n: int = 3):
+    """assemblies/s of ONE oracle process (single-core figure beside the all-core one)."""
+    import oracle_lib as ol
+
+    odb = ol.OracleDB(*db.flat())
+    t0 = time.perf_counter()
+    for f in asms_flat[:n]:
+        odb.map(*f)
+    return min(n, len(asms_flat)) / (time.perf_counter() - t0)
+
+
+PARITY_FIELDS = ("gene", "q_start", "q_end", "t_ctg", "t_len", "t_start", "t_end", "strand", "score", "matches", "block_len",
+                 "edit_distance", "mapq", "is_primary")
+
+
+def parity_check(res, oracle_res: dict) -> dict:
+    """Field-by-field + CIGAR comparison of the GPU step's hits with the oracle's for the same assemblies."""
+    asm = res.hits["asm_id"]
+    mismatches, n_hits, bad = 0, 0, []
+    for ai, (oh, oc) in sorted(oracle_res.items()):
+        lo, hi = np.searchsorted(asm, ai, "left"), np.searchsorted(asm, ai, "right")
+        ok = (hi - lo) == len(oh)
+        if ok:
+            for f in PARITY_FIELDS:
+                if not np.array_equal(res.hits[f][lo:hi].astype(np.int64), oh[f].astype(np.int64)):
+                    ok = False
+                    break
+        if ok:
+            co, nc = res.hits["cigar_off"][lo:hi], res.hits["n_cigar"][lo:hi]
+            ok = np.array_equal(nc.astype(np.int64), oh["n_cigar"].astype(np.int64))
+            if ok and len(oh):
+                g = np.concatenate([res.cigar[int(o) : int(o) + int(n)] for o, n in zip(co, nc)]) if len(co) else np.zeros(0, np.uint32)
+                w = np.concatenate([oc[int(o) : int(o) + int(n)] for o, n in zip(oh["cigar_off"], oh["n_cigar"])])
+                ok = np.array_equal(g, w)
+        n_hits += len(oh)
+        if not ok:
+            mismatches += 1
+            bad.append(int(ai))
+    return {"parity_checked": len(oracle_res), "mismatches": mismatches, "hits_compared": int(n_hits), "mismatched_assemblies": bad[:8]}
+
+
+def sample_size(a, cores: int) -> int:
+    return a.cpu_sample or max(2, min(4 * cores, 96))
+
+
+def reference_sample(a, db, ranges, n: int):
+    """The first n assemblies of the GPU arm's workload as host arrays.  They are drawn on the GPU (torch RNG), so the reference arm
+    uses the device for data generation only; without one it falls back to the numpy generator (different sequences, same shape)."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from kaptive_b200 import workload
+
+            wl = workload.make_device_workload(db, n, a.asm_len, seed=1000, device="cuda:0", locus_ranges=ranges)
+            out = [wl.host_assembly(i) for i in range(n)]
+            del wl
+            torch.cuda.empty_cache()
+            return out, "the first %d assemblies of the GPU arm's workload (same seeds, same bytes)" % n
+    except Exception:
+        pass
     from kaptive_b200 import synth
 
     out = []
-    n_real = int(db.gene_locus[~db.extra].max() + 1)
     for i in range(n):
         rng = np.random.default_rng(1000 + i)
-        asm = synth.make_assembly(db, int(rng.integers(0, n_real)), seed=1000 + i, genome_len=a.asm_len)
-        out.append(asm.flat())
-    return out
+        pick = [int(rng.integers(l0, l1)) for l0, l1 in (ranges or ((0, a.n_loci),))]
+        out.append(synth.make_assembly(db, pick[0], seed=1000 + i, genome_len=a.asm_len, extra_loci=tuple(pick[1:])).flat())
+    return out, "%d assemblies of the same generator family (no CUDA device: numpy generator)" % n
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from kaptive_b200 import synth
-
     cores = os.cpu_count() or 1
-    db = synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1)
-    n = a.cpu_sample or max(2, min(4 * cores, 96))
-    sample = host_sample(a, db, n)
+    db, ranges = make_db(a)
+    n = a.cpu_sample or max(2 * cores, min(12 * cores, 192))  # BASELINE.md section 3: N >= 200 where the cores allow it in minutes
+    sample, what = reference_sample(a, db, ranges, n)
+    single = cpu_single_core(db, sample, 3)
     for _ in range(min(a.warmup, 1)):
-        cpu_oracle_rate(db, sample[: max(1, min(cores, n))], cores)
+        cpu_oracle_run(db, sample[: max(1, min(cores, n))], cores)
     rates, secs = [], []
     for _ in range(a.steps):
-        r, s = cpu_oracle_rate(db, sample, cores)
+        r, s, _res = cpu_oracle_run(db, sample, cores)
         rates.append(r), secs.append(s)
     v = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} assemblies per step"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} x {a.asm_len / 1e6:g} Mb assemblies, oracle/kb_oracle.c, one process per core"},
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} assemblies per step: {what}"},
+        "cpu_baseline": {"value": v, "best": float(np.max(rates)), "single_core": single, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} x {a.asm_len / 1e6:g} Mb assemblies, oracle/kb_oracle.c (-O3 -march=x86-64-v3, scalar DP where "
+                                   "minimap2 / rammappy use SSE ksw2), one process per core"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference mapper (rammappy, closed Rust wheel) is not installable offline; this arm times the C port of its algorithm",
     }
@@ -198,7 +283,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
 
-    db = synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1)
+    db, ranges = make_db(a)
     # gene index: built on rank 0, broadcast once as a flat byte image over NCCL
     if world > 1:
         if rank == 0:
@@ -215,8 +300,13 @@ def run_ours(a):
     else:
         gi = mapper.GeneIndex(db.genes, device=local)
 
-    wl = workload.make_device_workload(db, a.n_asm, a.asm_len, seed=1000, device=dev, first_index=rank * a.n_asm)
+    wl = workload.make_device_workload(db, a.n_asm, a.asm_len, seed=1000, device=dev, first_index=rank * a.n_asm, locus_ranges=ranges)
     torch.cuda.synchronize()
+    # the CPU leg maps the SAME first assemblies the GPU step maps: taken off the device workload before it is dropped
+    cpu_cores = os.cpu_count() or 1
+    cpu_asms = []
+    if rank == 0 and not a.no_cpu_baseline:
+        cpu_asms = [wl.host_assembly(i) for i in range(min(sample_size(a, cpu_cores), a.n_asm))]
     batch = mapper.AssemblyBatch(wl.ascii.data_ptr(), wl.contig_off, wl.contig_len, wl.asm_contig_start, device=local)
     packed_bytes = batch.packed_bytes
 
@@ -268,11 +358,13 @@ def run_ours(a):
     stage_acc = {}
     counters = {}
     n_hits = 0
+    last_res = None
     t0 = time.perf_counter()
     for _ in range(a.steps):
         res = gi.map(batch, fetch=True, out=out)
         n_hits = len(res)
         counters = res.counters
+        last_res = res
         for k, v in res.stage_ms.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     barrier()
@@ -319,19 +411,22 @@ def run_ours(a):
     # roofline of the scan kernel --------------------------------------------------------------------
     peak, peak_src = peaks()
     scan_ms = stage_acc.get("scan", 0.0) / a.steps
-    alg_bytes = packed_bytes + 12 * counters.get("anchors", 0)
+    alg_bytes = packed_bytes + ANCHOR_BYTES * counters.get("anchors", 0)
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    traffic = None  # dram read + write bytes of one scan launch from the committed ncu --set full capture of this workload
+    # dram read + write bytes of one scan launch: NOT measured by this run (that needs ncu); taken from the committed ncu --set full
+    # capture of the same command line when its shape matches, else null
+    traffic, traffic_src = None, "not measured in this run"
     try:
         t = json.loads((ROOT / "profiles" / "scan_traffic.json").read_text())
-        if int(t["assemblies_per_launch"]) == a.n_asm and int(t["asm_len"]) == a.asm_len:
+        if int(t["assemblies_per_launch"]) == a.n_asm and int(t["asm_len"]) == a.asm_len and t.get("db", "k") == a.db:
             traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+            traffic_src = "profiles/scan_traffic.json (ncu --set full capture of this workload, committed; not measured in this run)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "kb_scan_kernel<10,15>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": scan_ms,
-                "note": "the sketch is integer-issue bound (137 warp instructions per 32 positions, ALU pipe 60 % busy): see DESIGN.md section 4"}
+                "note": "2-bit sequence + N mask + 16 B per anchor; the sketch is integer-issue bound, not HBM bound: see DESIGN.md section 4"}
     align_ms = stage_acc.get("align", 0.0) / a.steps
     dominant = {"kernels": "kb_rows_kernel + kb_band_kernel (base-level DP)", "share_of_step": align_ms / dev_ms if dev_ms else None,
                 "dp_cells_per_step": int(counters.get("dp_cells", 0)),
@@ -340,16 +435,15 @@ def run_ours(a):
                 # the same kernels against the HBM roofline: algorithmic bytes = 1 B of traceback written per DP cell
                 "hbm": {"achieved": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 if align_ms else None, "peak": peak, "unit": "GB/s",
                         "frac": counters.get("dp_cells", 0) / (align_ms * 1e-3) / 1e9 / peak if align_ms and peak else None,
-                        "traffic": "ncu: 127 GB written per 1000 assemblies (profiles/ncu_r1_final_details.csv: 24.9 + 7.1 GB per 250)"}}
+                        "traffic": None}}
 
-    cpu = None
-    if not a.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n = a.cpu_sample or max(2, min(4 * cores, 96))  # about 10 s of CPU work on the box's cores
-        sample = host_sample(a, db, n)
-        rate, secs = cpu_oracle_rate(db, sample, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} x {a.asm_len / 1e6:g} Mb assemblies of the same generator, oracle/kb_oracle.c, one process per core, {secs:.1f} s"}
+    cpu, parity = None, {"parity_checked": 0, "mismatches": None}
+    if not a.no_cpu_baseline and cpu_asms:
+        rate, secs, ores = cpu_oracle_run(db, cpu_asms, cpu_cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+               "sample": f"the first {len(cpu_asms)} assemblies the GPU step mapped ({a.asm_len / 1e6:g} Mb each, same bytes), "
+                         f"oracle/kb_oracle.c, one process per core, {secs:.1f} s"}
+        parity = parity_check(last_res, ores)  # the timed step's own hits against the oracle's, field by field + CIGAR
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -369,6 +463,7 @@ def run_ours(a):
         "roofline": roofline,
         "dominant": dominant,
         "cpu_baseline": cpu,
+        **parity,
     }
     print(json.dumps(line), flush=True)
     if dist:

@@ -136,12 +136,20 @@ void kb_result_destroy(kb_result_t *r);
 /* per-stage device time of the call that produced `r`, CUDA events on its stream */
 enum { KB_STAGE_SCAN = 0, KB_STAGE_SORT, KB_STAGE_CHAIN, KB_STAGE_ALIGN, KB_STAGE_FINAL, KB_STAGE_TOTAL, KB_N_STAGES };
 int kb_result_stage_ms(const kb_result_t *r, float *ms /* KB_N_STAGES */);
-/* counters: [0] minimizers scanned-out, [1] anchors, [2] query groups, [3] chains, [4] raw hits, [5] kernel launches, [6] DP cells */
-int kb_result_counters(const kb_result_t *r, int64_t *c /* 8 */);
+/* counters: [0] minimizers scanned-out, [1] anchors, [2] query groups, [3] chains, [4] raw hits, [5] kernel launches, [6] DP cells,
+ * [7] chains the staged aligner handed to the one-warp aligner, [8] alignments DROPPED because they ran into an internal limit
+ * (chain window > 65536 target bases, CIGAR > 8192 operations): callers that need completeness must treat [8] != 0 as an error
+ * (the Python layer raises), [9..15] reserved */
+int kb_result_counters(const kb_result_t *r, int64_t *c /* 16 */);
 /* stage dumps for parity tests (device -> host); arrays of int32 records */
 int kb_result_fetch_anchors(const kb_result_t *r, int32_t *out /* n x 7: asm,gene,rev,rid,tpos,qpos,flags */, int64_t cap, int64_t *n);
 int kb_result_fetch_chains(const kb_result_t *r, int32_t *out /* n x 10: asm,gene,score,cnt,rev,rid,rs,re,qs,qe */, int64_t cap, int64_t *n);
 int kb_result_mid_occ(const kb_result_t *r, int32_t *out /* n_asm */);
+
+/* Returns the idle workspace arenas of `device` (-1: every device) to the CUDA allocator.  A mapping call keeps its scratch
+ * arena (tens of GB for large batches) for the life of the process so that steady-state calls never reach the allocator;
+ * a long-lived server calls this when it goes idle.  Arenas of calls in flight are untouched. */
+int kb_release_workspace(int device);
 
 /* diagnostic: calls / cells of the base-level DP per (kind, path) since the last reset, process-wide on the current
  * device; slot 2 * (5 * kind + path) = calls, + 1 = cells; kind 0 gap fill, 1 end extension, 2 gap fill with z-drop;

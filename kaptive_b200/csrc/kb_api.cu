@@ -47,7 +47,7 @@ void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, int32_
 void kb_launch_stage_assemble(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const void *,
                               const void *, const uint32_t *, uint32_t *, int64_t, KbRawHit *, int64_t, uint32_t *, int64_t, int32_t *,
                               unsigned long long *, cudaStream_t);
-void kb_launch_rawkey(const KbRawHit *, int64_t, uint64_t *, uint32_t *, cudaStream_t);
+void kb_launch_rawkey(const KbRawHit *, int64_t, uint64_t *, uint32_t *, unsigned long long *, cudaStream_t);
 void kb_launch_gather_raw(const KbRawHit *, const uint32_t *, int64_t, KbRawHit *, cudaStream_t);
 void kb_launch_finalize(const kb_params_t &, KbRawHit *, int64_t, const KbGroupInfo *, int32_t *, uint64_t *, int32_t *, cudaStream_t);
 void kb_launch_scatter(const KbRawHit *, const int32_t *, const int64_t *, int64_t, const KbGroupInfo *, const KbBatchView &,
@@ -163,7 +163,7 @@ struct kb_batch {
     uint8_t *d_blob = nullptr;  // layout arrays
     uint32_t *seq2 = nullptr, *nmask = nullptr;
     KbBatchView view;
-    int64_t last_anchor_count = 0;  // sizing hint for repeated calls on the same batch
+    std::atomic<int64_t> last_anchor_count{0};  // sizing hint for repeated calls on the same batch (the only mutable field; relaxed)
 };
 
 struct kb_result {
@@ -174,7 +174,7 @@ struct kb_result {
     uint32_t *pool = nullptr;
     std::vector<void *> owned;
     float stage_ms[KB_N_STAGES] = {0};
-    int64_t counters[8] = {0};
+    int64_t counters[16] = {0};
     std::vector<int32_t> mid_occ;
     // stage dumps
     int32_t *d_anchor_dump = nullptr;
@@ -388,6 +388,7 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         CU(cudaStreamDestroy(st));
     } catch (const std::string &e) {
         if (st) cudaStreamSynchronize(st), cudaStreamDestroy(st);
+        if (d_ascii) cudaFreeAsync(d_ascii, 0);
         if (b->d_blob) cudaFreeAsync(b->d_blob, 0);
         if (b->seq2) cudaFreeAsync(b->seq2, 0);
         if (b->nmask) cudaFreeAsync(b->nmask, 0);
@@ -463,10 +464,16 @@ static int32_t census_one(const kb_index *ix, const kb_batch *bt, int asm_id, De
         CU(cudaMemcpyAsync(&n_runs, d_n, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(kb_sort_keys32(tmp, tb, cnt, cnt2, n_runs, 32, st));
-        uint32_t kth = (uint32_t)((1. - p.mid_occ_frac) * (double)n_runs), val = 0;
-        CU(cudaMemcpyAsync(&val, cnt2 + kth, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        mid = (int32_t)(val + 1);
+        if (p.mid_occ_frac <= 0.f || n_runs <= 0) mid = INT32_MAX;  // [mm2:index.c:mm_idx_cal_max_occ] f <= 0: no cut-off
+        else {
+            int64_t kth = (int64_t)((1. - p.mid_occ_frac) * (double)n_runs);
+            if (kth > n_runs - 1) kth = n_runs - 1;
+            if (kth < 0) kth = 0;
+            uint32_t val = 0;
+            CU(cudaMemcpyAsync(&val, cnt2 + kth, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            mid = (int32_t)(val + 1);
+        }
         P.release(tmp);
     }
     if (mid < p.min_mid_occ) mid = p.min_mid_occ;
@@ -499,7 +506,8 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         unsigned long long hc[KB_N_COUNTERS];
 
         // ---------------- scan (+ rerun once if the anchor buffer was too small)
-        int64_t anchor_cap = bt->last_anchor_count > 0 ? bt->last_anchor_count + bt->last_anchor_count / 16 + 1024 : bv.total_bases / 48 + (1 << 20);
+        const int64_t hint = bt->last_anchor_count.load(std::memory_order_relaxed);
+        int64_t anchor_cap = hint > 0 ? hint + hint / 16 + 1024 : bv.total_bases / 48 + (1 << 20);
         uint64_t *akey = nullptr;
         uint32_t *aval = nullptr;
         int64_t n_anchors = 0;
@@ -519,7 +527,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             P.release(akey), P.release(aval);
             anchor_cap = n_anchors + n_anchors / 16 + 1024;
         }
-        bt->last_anchor_count = n_anchors;
+        bt->last_anchor_count.store(n_anchors, std::memory_order_relaxed);
         if (n_anchors >= ((int64_t)1 << 31)) throw std::string("more than 2^31 anchors in one batch: split the batch");
         CU(cudaEventRecord(ev[1], st));
         R->counters[0] = (int64_t)hc[0], R->counters[1] = n_anchors;
@@ -724,7 +732,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         if (n_raw > 0) {
             uint64_t *rk = P.get<uint64_t>((size_t)n_raw), *rk2 = P.get<uint64_t>((size_t)n_raw);
             uint32_t *ri = P.get<uint32_t>((size_t)n_raw), *ri2 = P.get<uint32_t>((size_t)n_raw);
-            kb_launch_rawkey(raw, n_raw, rk, ri, st);
+            kb_launch_rawkey(raw, n_raw, rk, ri, d_counters + 15, st);  // [15]: raw hits that carry an internal-limit error
             size_t tb = kb_sort_pairs_temp_bytes(n_raw), tb2 = kb_scan_temp_bytes(n_raw);
             if (tb2 > tb) tb = tb2;
             uint8_t *tmp = P.get<uint8_t>(tb);
@@ -739,8 +747,11 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             int32_t last_k = 0;
             CU(cudaMemcpyAsync(&last_o, oidx + n_raw - 1, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(&last_k, keep + n_raw - 1, 4, cudaMemcpyDeviceToHost, st));
+            unsigned long long n_err = 0;
+            CU(cudaMemcpyAsync(&n_err, d_counters + 15, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             n_hits = last_o + last_k;
+            R->counters[8] = (int64_t)n_err;
         }
         R->n_hits = n_hits;
         {
@@ -986,6 +997,24 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
     return rc;
 }
 
+int kb_release_workspace(int device)
+{
+    std::vector<Arena *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        for (size_t i = g_arenas.size(); i-- > 0;)
+            if (device < 0 || g_arenas[i]->device == device) drop.push_back(g_arenas[i]), g_arenas.erase(g_arenas.begin() + (long)i);
+    }
+    for (Arena *a : drop) {
+        if (a->base) {
+            cudaSetDevice(a->device);
+            cudaFree(a->base);
+        }
+        delete a;
+    }
+    return KB_OK;
+}
+
 int kb_scan_minimizers(const kb_index_t *ix, const kb_batch_t *bt, int32_t asm_id, uint32_t *hash, int32_t *ctg, uint32_t *pos_strand,
                        int64_t cap, int64_t *n)
 {
@@ -1034,7 +1063,8 @@ int kb_bench_scan(const kb_index_t *ix, const kb_batch_t *bt, int iters, float *
         P.st = st;
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
-        int64_t cap = bt->last_anchor_count > 0 ? bt->last_anchor_count + 1024 : bt->view.total_bases / 48 + (1 << 20);
+        const int64_t hint = bt->last_anchor_count.load(std::memory_order_relaxed);
+        int64_t cap = hint > 0 ? hint + 1024 : bt->view.total_bases / 48 + (1 << 20);
         unsigned long long *dc = P.get<unsigned long long>(KB_N_COUNTERS);
         uint64_t *akey = P.get<uint64_t>((size_t)cap);
         uint32_t *aval = P.get<uint32_t>((size_t)cap);

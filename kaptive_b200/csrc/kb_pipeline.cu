@@ -504,10 +504,11 @@ void kb_launch_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, cons
 }
 
 // ------------------------------------------------------------------ finalisation
-__global__ void kb_rawkey_kernel(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx)
+__global__ void kb_rawkey_kernel(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx, unsigned long long *n_err)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const KbRawHit &h = raw[i];
+        if (h.err) atomicAdd(n_err, 1ull);  // an alignment that ran into an internal limit: dropped by the finaliser, counted here
         key[i] = (uint64_t)(uint32_t)h.group << 32 | (uint64_t)(h.reg_idx & 0xfffff) << 12 | (uint64_t)(h.split_idx & 0xfff);
         idx[i] = (uint32_t)i;
     }
@@ -551,9 +552,9 @@ __global__ void kb_scatter_kernel(const KbRawHit *hits, const int32_t *keep_flag
     }
 }
 
-void kb_launch_rawkey(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx, cudaStream_t st)
+void kb_launch_rawkey(const KbRawHit *raw, int64_t n, uint64_t *key, uint32_t *idx, unsigned long long *n_err, cudaStream_t st)
 {
-    if (n > 0) kb_rawkey_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, n, key, idx);
+    if (n > 0) kb_rawkey_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, n, key, idx, n_err);
 }
 void kb_launch_gather_raw(const KbRawHit *raw, const uint32_t *idx, int64_t n, KbRawHit *out, cudaStream_t st)
 {

@@ -22,6 +22,11 @@ from . import _lib
 from ._lib import HIT_FIELDS, KB_N_STAGES, STAGE_NAMES, KbHits, KbParams, check, ptr
 
 
+import os
+
+_ALLOW_LIMIT_DROPS = os.environ.get("KAPTIVE_B200_ALLOW_LIMIT_DROPS", "0") == "1"
+
+
 def _flat(seqs: list[bytes]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     lengths = np.fromiter((len(s) for s in seqs), dtype=np.int32, count=len(seqs))
     offsets = np.zeros(len(seqs), dtype=np.int64)
@@ -203,7 +208,7 @@ def _drain(L, r, n_asm: int, fetch: bool, out=None) -> MapResult:
     nh, nc = C.c_int64(0), C.c_int64(0)
     check(L.kb_result_size(r, C.byref(nh), C.byref(nc)))
     ms = np.zeros(KB_N_STAGES, dtype=np.float32)
-    cnt = np.zeros(8, dtype=np.int64)
+    cnt = np.zeros(16, dtype=np.int64)
     check(L.kb_result_stage_ms(r, ptr(ms)))
     check(L.kb_result_counters(r, ptr(cnt)))
     mid = np.zeros(max(n_asm, 1), dtype=np.int32)
@@ -229,7 +234,10 @@ def _drain(L, r, n_asm: int, fetch: bool, out=None) -> MapResult:
     if n.value:
         chains = np.zeros((n.value, 10), dtype=np.int32)
         check(L.kb_result_fetch_chains(r, ptr(chains), n.value, C.byref(n)))
-    names = ("minimizers", "anchors", "groups", "chains", "raw_hits", "launches", "dp_cells", "slow_chains")
+    names = ("minimizers", "anchors", "groups", "chains", "raw_hits", "launches", "dp_cells", "slow_chains", "limit_drops")
+    if int(cnt[8]) and not _ALLOW_LIMIT_DROPS:
+        raise _lib.KbError(f"{int(cnt[8])} alignment(s) ran into an internal limit (chain window > 65536 bases or CIGAR > 8192 operations) "
+                           "and were dropped; set KAPTIVE_B200_ALLOW_LIMIT_DROPS=1 to accept incomplete results")
     return MapResult(
         hits=hits,
         cigar=cigar,

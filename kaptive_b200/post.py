@@ -81,16 +81,24 @@ def _local_order(keys: tuple, seg_off: np.ndarray) -> np.ndarray:
     return order
 
 
-def cull_overlaps(starts, ends, group1, group2, scores, matches, mapq, seg_off, max_overlap_fraction: float = 0.1,
-                  priority_mask=None) -> np.ndarray:
-    """``Alignments.cull_overlaps`` (reference core/alignment.py:643-686) for the hits of many assemblies at once: evaluation order
-    = score (+1e9 where ``priority_mask``), then matches, then mapq, all descending (:669-675); returns the boolean kept mask."""
-    L = _lib.load()
-    seg_off = np.ascontiguousarray(seg_off, np.int64)
+def cull_order(scores, matches, mapq, seg_off, priority_mask=None) -> np.ndarray:
+    """Evaluation order of ``Alignments.cull_overlaps`` per segment: ``np.lexsort((-qualities, -matches, -scores))`` (reference
+    core/alignment.py:669-675).  ``qualities`` is uint8 there (core/alignment.py:466), so its negation WRAPS: among hits that tie on
+    score and matches, mapq 0 sorts first, then 255, 254, ... 1 -- reproduced with the same uint8 arithmetic.  Host-only."""
     sc = np.asarray(scores, np.float64).copy()
     if priority_mask is not None:
         sc[np.asarray(priority_mask, bool)] += 1e9
-    order = _local_order((-np.asarray(mapq).astype(np.int32), -np.asarray(matches).astype(np.int64), -sc), seg_off)
+    return _local_order((-np.asarray(mapq).astype(np.uint8), -np.asarray(matches).astype(np.int32), -sc), np.asarray(seg_off, np.int64))
+
+
+def cull_overlaps(starts, ends, group1, group2, scores, matches, mapq, seg_off, max_overlap_fraction: float = 0.1,
+                  priority_mask=None) -> np.ndarray:
+    """``Alignments.cull_overlaps`` (reference core/alignment.py:643-686) for the hits of many assemblies at once: evaluation order
+    = :func:`cull_order` (score + 1e9 where ``priority_mask``, then matches, then the wrapped uint8 mapq).  Returns the boolean
+    kept mask."""
+    L = _lib.load()
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    order = cull_order(scores, matches, mapq, seg_off, priority_mask)
     a = [np.ascontiguousarray(x, np.int32) for x in (group1, group2, starts, ends)]
     kept = np.zeros(max(int(seg_off[-1]), 1), np.uint8)
     _check(L.kb_post_cull_overlaps(ptr(order), ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), float(max_overlap_fraction), ptr(seg_off),

@@ -193,6 +193,34 @@ def make_db(
     )
 
 
+def combine(*dbs: SynthDB) -> SynthDB:
+    """Several gene sets in ONE index, loci renumbered consecutively (BASELINE.json configs[2]: kpsc_k + kpsc_o combined)."""
+    genes, loci, names, gnames = [], [], [], []
+    cols = {k: [] for k in ("gene_locus", "gene_pos", "gene_start", "gene_end", "gene_strand", "extra")}
+    for d in dbs:
+        base = len(loci)
+        genes += d.genes
+        loci += d.loci
+        names += d.locus_names
+        gnames += d.gene_names
+        cols["gene_locus"].append(d.gene_locus + base)
+        for k in ("gene_pos", "gene_start", "gene_end", "gene_strand", "extra"):
+            cols[k].append(getattr(d, k))
+    c = {k: np.concatenate(v) for k, v in cols.items()}
+    return SynthDB(genes=genes, gene_locus=c["gene_locus"].astype(np.int32), gene_pos=c["gene_pos"], gene_start=c["gene_start"],
+                   gene_end=c["gene_end"], gene_strand=c["gene_strand"], extra=c["extra"], loci=loci, locus_names=names, gene_names=gnames)
+
+
+def make_ko_db(k_loci: int = 150, k_genes: int = 20, k_core: int = 4, o_loci: int = 20, o_genes: int = 10, o_core: int = 2,
+               o_extra: int = 15, seed: int = 1) -> tuple[SynthDB, tuple[tuple[int, int], ...]]:
+    """kpsc_k-shaped + kpsc_o-shaped gene sets in one index: 150 x 20 K genes with 4 core families,
+    20 x 10 O genes with 2 core families + 15 "Extra genes" records.  Returns the database and, per locus class, the half-open range
+    of locus indices an assembly draws its embedded locus from ((0, 150) for K, (150, 170) for O)."""
+    k = make_db(n_loci=k_loci, genes_per_locus=k_genes, n_core=k_core, seed=seed, prefix="KL")
+    o = make_db(n_loci=o_loci, genes_per_locus=o_genes, n_core=o_core, n_extra=o_extra, seed=seed + 1, prefix="OL")
+    return combine(k, o), ((0, k_loci), (k_loci, k_loci + o_loci))
+
+
 @dataclass
 class SynthAssembly:
     name: str

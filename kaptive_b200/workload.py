@@ -2,6 +2,8 @@
 
 ``configs[1]``: 1,000 synthetic 5 Mb Klebsiella-like assemblies vs a kpsc_k-shaped database
 (150 loci x 20 genes, 4 core gene families shared by all loci) on one B200.
+``configs[2]`` (the configuration the metric is quoted on): 10,000 assemblies vs kpsc_k + kpsc_o in ONE index
+(``synth.make_ko_db``), a K locus and an O locus embedded in every assembly (``locus_ranges``).
 
 The 5 Gbase of background sequence are drawn with torch on the GPU (numpy would take minutes);
 the embedded locus of each assembly is mutated on the host (small) and copied in.  torch is used
@@ -23,15 +25,25 @@ class DeviceWorkload:
     contig_off: np.ndarray  # int64
     contig_len: np.ndarray  # int32
     asm_contig_start: np.ndarray  # int32, n_asm + 1
-    locus: np.ndarray  # embedded locus per assembly
+    locus: np.ndarray  # embedded loci per assembly, [n_asm, n_classes] (K locus, O locus, ...)
     n_asm: int
     asm_len: int
+
+    def host_assembly(self, a: int) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Assembly `a` as host arrays (ASCII bytes, int64 contig offsets, int32 lengths): what the CPU legs of bench.py map, so
+        that they see exactly the sequences the GPU step mapped."""
+        seq = self.ascii[a * self.asm_len : (a + 1) * self.asm_len].cpu().numpy()
+        c0, c1 = int(self.asm_contig_start[a]), int(self.asm_contig_start[a + 1])
+        return seq, (self.contig_off[c0:c1] - a * self.asm_len).astype(np.int64), self.contig_len[c0:c1].astype(np.int32)
 
 
 def make_device_workload(db: synth.SynthDB, n_asm: int, asm_len: int = 5_000_000, mean_contigs: float = 80.0,
                          seed: int = 1000, device: str = "cuda:0", gc: float = 0.57, n_frac: float = 1e-4,
                          sub: tuple[float, float] = (0.0, 0.05), indel: tuple[float, float] = (0.0, 0.005),
-                         first_index: int = 0) -> DeviceWorkload:
+                         first_index: int = 0, locus_ranges: tuple[tuple[int, int], ...] | None = None) -> DeviceWorkload:
+    """Assembly `first_index + a` is a pure function of (seed, first_index + a, asm_len): the background is drawn in fixed chunks
+    of `step` assemblies whose generator seed depends on the chunk's first global index only, so a rank, a smaller sample (the CPU
+    arm) and the full batch all see the same sequences for the same global assembly index."""
     import torch
 
     dev = torch.device(device)
@@ -40,31 +52,43 @@ def make_device_workload(db: synth.SynthDB, n_asm: int, asm_len: int = 5_000_000
     gen = torch.Generator(device=dev)
     thr = torch.tensor([(1 - gc) / 2, 0.5, 0.5 + gc / 2], device=dev)  # A | C | G | T cumulative
     step = max(1, (256 << 20) // asm_len)
-    for a0 in range(0, n_asm, step):
-        a1 = min(n_asm, a0 + step)
-        gen.manual_seed(seed * 1_000_003 + first_index + a0)
-        u = torch.rand((a1 - a0) * asm_len, device=dev, generator=gen)
+    # chunks are aligned to multiples of `step` in GLOBAL assembly indices and always drawn at full size
+    g_lo, g_hi = first_index, first_index + n_asm
+    for c0 in range(g_lo - g_lo % step, g_hi, step):
+        gen.manual_seed(seed * 1_000_003 + c0)
+        u = torch.rand(step * asm_len, device=dev, generator=gen)
         codes = torch.bucketize(u, thr).to(torch.uint8)
         # order A,C,G,T with P(C)=P(G)=gc/2: buckets [0,(1-gc)/2) A, [.., .5) C, [.5, .5+gc/2) G, rest T
-        seg = out[a0 * asm_len : a1 * asm_len]
-        seg.copy_(lut[codes.long()])
-        if n_frac > 0:
-            m = torch.rand(seg.numel(), device=dev, generator=gen) < n_frac
-            seg[m] = ord("N")
+        chunk = lut[codes.long()]
         del u, codes
-    loci = np.zeros(n_asm, dtype=np.int32)
-    ctg_off, ctg_len, acs = [], [], [0]
+        if n_frac > 0:
+            m = torch.rand(step * asm_len, device=dev, generator=gen) < n_frac
+            chunk[m] = ord("N")
+            del m
+        lo, hi = max(c0, g_lo), min(c0 + step, g_hi)
+        out[(lo - g_lo) * asm_len : (hi - g_lo) * asm_len] = chunk[(lo - c0) * asm_len : (hi - c0) * asm_len]
+        del chunk
     n_real_loci = int((~db.extra).sum() and (db.gene_locus[~db.extra].max() + 1))
+    if locus_ranges is None:
+        locus_ranges = ((0, n_real_loci),)
+    loci = np.zeros((n_asm, len(locus_ranges)), dtype=np.int32)
+    ctg_off, ctg_len, acs = [], [], [0]
     for a in range(n_asm):
         rng = np.random.default_rng(seed + first_index + a)
-        li = int(rng.integers(0, n_real_loci))
-        loci[a] = li
-        ls = np.frombuffer(db.loci[li], dtype=np.uint8)
-        ls = synth.mutate(rng, ls, float(rng.uniform(*sub)), float(rng.uniform(*indel)))
-        if rng.random() < 0.5:
-            ls = synth.revcomp(ls)
-        pos = int(rng.integers(0, asm_len - len(ls)))
-        out[a * asm_len + pos : a * asm_len + pos + len(ls)] = torch.from_numpy(ls.copy()).to(dev)
+        taken: list[tuple[int, int]] = []
+        for ci, (l0, l1) in enumerate(locus_ranges):
+            li = int(rng.integers(l0, l1))
+            loci[a, ci] = li
+            ls = np.frombuffer(db.loci[li], dtype=np.uint8)
+            ls = synth.mutate(rng, ls, float(rng.uniform(*sub)), float(rng.uniform(*indel)))
+            if rng.random() < 0.5:
+                ls = synth.revcomp(ls)
+            while True:  # embedded loci never overlap
+                pos = int(rng.integers(0, asm_len - len(ls)))
+                if all(pos + len(ls) <= s0 or pos >= s1 for s0, s1 in taken):
+                    break
+            taken.append((pos, pos + len(ls)))
+            out[a * asm_len + pos : a * asm_len + pos + len(ls)] = torch.from_numpy(ls.copy()).to(dev)
         n_ctg = max(1, int(rng.poisson(mean_contigs)))
         bps = np.unique(rng.integers(1, asm_len, size=n_ctg - 1)) if n_ctg > 1 else np.zeros(0, dtype=np.int64)
         bounds = np.concatenate([[0], bps, [asm_len]]).astype(np.int64)

@@ -5,7 +5,7 @@
 
 Inputs are random hit tables shaped like one assembly's alignments (10..600 hits on a few contigs / genes); outputs
 come from the reference's own numba kernels, driven exactly as the reference drives them:
-  cull    : order = np.lexsort((-mapq, -matches, -scores))            (core/alignment.py:669-675)
+  cull    : order = np.lexsort((-mapq, -matches, -scores)), mapq uint8 so the negation wraps (core/alignment.py:466,669-675)
             _cull_overlaps_kernel(order, group1, group2, starts, ends, frac, n)   (core/interval.py:698-751)
   cluster : order = np.lexsort((ends, starts, groups))                 (core/interval.py:492)
             _cluster_kernel(starts, ends, groups, tolerance, order)    (core/interval.py:595-639)
@@ -38,7 +38,12 @@ def main():
         if n > 4:  # exact ties in every key
             score[1], matches[1], mapq[1] = score[0], matches[0], mapq[0]
             score[3] = score[2]
-        order_cull = np.lexsort((-mapq.astype(np.int32), -matches, -score)).astype(np.int32)
+        if n > 8:  # overlapping duplicate hits that tie on score and matches: a primary (mapq > 0) against a secondary (mapq 0)
+            for a, b in ((4, 5), (6, 7)):
+                g1[b], g2[b], st[b], en[b] = g1[a], g2[a], st[a] + 3, en[a] + 3
+                score[b], matches[b] = score[a], matches[a]
+            mapq[4], mapq[5], mapq[6], mapq[7] = 37, 0, 0, 12
+        order_cull = np.lexsort((-mapq, -matches, -score)).astype(np.int32)  # uint8 negation, exactly as Alignments.cull_overlaps
         frac = float(rng.choice([0.1, 0.0, 0.5]))
         kept = _cull_overlaps_kernel(order_cull, g1, g2, st, en, frac, n) if n else np.zeros(0, bool)
         tol = int(rng.choice([0, 100, 30000]))

@@ -106,6 +106,24 @@ def test_oracle_cull_batched_equals_per_segment():
     assert np.array_equal(kept, cat("kept"))
 
 
+def test_cull_order_is_the_reference_lexsort_with_wrapped_uint8_mapq():
+    """kaptive_b200.post.cull_order vs the order the reference's own Alignments.cull_overlaps expression produced
+    (core/alignment.py:675 negates a uint8 array: mapq 0 sorts first among hits that tie on score and matches; the golden
+    set holds overlapping primary / secondary pairs in exactly that situation)."""
+    from kaptive_b200 import post
+
+    n_tied = 0
+    for s, sl in _a8_segments():
+        so = np.array([0, sl.stop - sl.start], np.int64)
+        order = post.cull_order(A8["score"][sl], A8["matches"][sl], A8["mapq"][sl], so)
+        assert np.array_equal(order, A8["order_cull"][sl]), s
+        if sl.stop - sl.start > 8:
+            pos = {int(v): i for i, v in enumerate(order)}
+            assert pos[5] < pos[4] and pos[6] < pos[7]  # the mapq-0 hit of each tied pair is evaluated first
+            n_tied += 1
+    assert n_tied > 20
+
+
 @pytest.mark.gpu
 def test_gpu_cull_and_cluster_match_reference_kernels():
     """CUDA kernels through kaptive_b200.post (which also derives the evaluation order the way the reference does) against
