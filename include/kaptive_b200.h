@@ -156,6 +156,15 @@ int kb_release_workspace(int device);
  * path 0 band certified, 1 band rejected, 2 register single pass, 3 register tiled, 4 scratch-memory DP. */
 int kb_debug_dp_stats(int64_t *out32, int reset);
 
+/* diagnostic / parity tests: runs n independent base-level DP problems (nt4 codes 0..4, concatenated) through ONE of the DP
+ * kernels: mode 0 scratch-memory DP (the form closest to oracle/kb_oracle.c:extd2), 1 row-stripe wavefront, 2 packed 16-bit
+ * row-stripe wavefront, 3 certified 64-diagonal band pass.  flag: KB_EZ_* bits (1 extension only, 2 right-aligned gaps,
+ * 4 reversed CIGAR, 8 global without z-drop).  out: n x 8 int32 = score, max, max_t, max_q, zdropped, n_cigar, ran (0: the
+ * kernel is not eligible for this problem, 2: band pass not certified), 0; cig: n x cig_stride BAM-encoded operations. */
+int kb_debug_dp(const kb_params_t *params, int device, const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t,
+                const int64_t *t_off, const int32_t *t_len, const int32_t *flag, const int32_t *w, const int32_t *zdrop, int32_t n,
+                int32_t mode, int32_t *out, uint32_t *cig, int32_t cig_stride);
+
 /* one-call convenience for HOST buffers (the end-to-end path): batch_create +
  * map + fetch + destroy; copies are inside. */
 int kb_map_assemblies(const kb_index_t *idx,

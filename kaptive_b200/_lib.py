@@ -84,6 +84,7 @@ _SYMBOLS = [
     ("kb_result_mid_occ", C.c_int, [_P, _P]),
     ("kb_release_workspace", C.c_int, [C.c_int]),
     ("kb_debug_dp_stats", C.c_int, [_P, C.c_int]),
+    ("kb_debug_dp", C.c_int, [C.POINTER(KbParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32]),
     ("kb_map_assemblies", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(KbHits), _P, _P, C.c_int64, _P]),
     ("kb_scan_minimizers", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     ("kb_bench_scan", C.c_int, [_P, _P, C.c_int, _P, _P]),

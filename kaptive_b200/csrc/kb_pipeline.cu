@@ -264,16 +264,28 @@ void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChain
 // The rows kernel's queue has two ends: rectangles of at least big_thr cells are stored from the back of the list and taken
 // first (longest jobs first keeps the tail of the persistent kernel short), the others from the front in planning order.
 #define KB_SC_ROWS_BIG 34
-__device__ __forceinline__ void kb_rows_enqueue(int32_t *rows_list, int64_t job_cap, unsigned long long *counters, int64_t big_thr, const KbJob &J,
-                                                int32_t jid)
+// the packed 16-bit wavefront (kb_rows16) has its own queue and kernel: rectangles it is eligible for go there
+#define KB_SC_R16 35
+#define KB_SC_R16_BIG 36
+#define KB_SC_QR16 37
+struct KbRowsQueues {
+    int32_t *rows_list, *r16_list;
+    int64_t job_cap, big_thr;
+    int use16;
+};
+__device__ __forceinline__ void kb_rows_enqueue(const KbRowsQueues &Q, const KbDpConst &P, unsigned long long *counters, const KbJob &J, int32_t jid)
 {
-    if (big_thr > 0 && (int64_t)J.qlen * J.tlen >= big_thr) rows_list[job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_ROWS_BIG], 1ull)] = jid;
-    else rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
+    const bool big = Q.big_thr > 0 && (int64_t)J.qlen * J.tlen >= Q.big_thr;
+    if (Q.use16 && kb_rows16_eligible(P, J.qlen, J.tlen, J.w)) {
+        if (big) Q.r16_list[Q.job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_R16_BIG], 1ull)] = jid;
+        else Q.r16_list[atomicAdd(&counters[KB_SC_R16], 1ull)] = jid;
+    } else if (big) Q.rows_list[Q.job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_ROWS_BIG], 1ull)] = jid;
+    else Q.rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
 }
 __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
                                                       const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, int32_t *kscratch,
-                                                      KbPlan *plans, KbJob *jobs, int64_t job_cap, int32_t *band_list, int32_t *rows_list,
-                                                      int32_t *slow_list, unsigned long long *counters, int64_t big_thr)
+                                                      KbPlan *plans, KbJob *jobs, int64_t job_cap, int32_t *band_list, KbRowsQueues Q,
+                                                      int32_t *slow_list, unsigned long long *counters)
 {
     const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_chains) return;
@@ -300,11 +312,12 @@ __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchVie
     kb_stage_plan(ix, bt, gi.asm_id, gi.gene, c.as, c.cnt, c.mlen, gi.n_a, ax, ay, K, pl, write);
     pl.job_base = base;
     plans[ci] = pl;
+    const KbDpConst P = kb_dp_const(ix.p);
     for (int k = 0; k < nj; ++k) {
         const KbJob &J = jobs[base + k];
         const bool band = J.kind == KB_JOB_FILL && J.qlen + J.tlen <= 8184 && kb_band_eligible(ix.p.max_sw_cells, J.qlen, J.tlen, J.w, J.flag);
         if (band) band_list[atomicAdd(&counters[KB_SC_BAND], 1ull)] = (int32_t)(base + k);
-        else kb_rows_enqueue(rows_list, job_cap, counters, big_thr, J, (int32_t)(base + k));
+        else kb_rows_enqueue(Q, P, counters, J, (int32_t)(base + k));
     }
 }
 
@@ -332,9 +345,9 @@ static __device__ __forceinline__ void kb_job_finish(int lane, KbJob *J, const K
 #ifndef KB_BAND_MINB
 #define KB_BAND_MINB 6
 #endif
-__global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, int32_t *rows_list,
+__global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *band_list, KbRowsQueues Q,
                                                         uint8_t *scratch, size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
-                                                        unsigned long long *counters, int64_t big_thr)
+                                                        unsigned long long *counters)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView 
             }
         }
         if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
-        else if (lane == 0) kb_rows_enqueue(rows_list, jobcig_cap / 16, counters, big_thr, *J, jid);
+        else if (lane == 0) kb_rows_enqueue(Q, P, counters, *J, jid);
     }
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
 }
@@ -413,6 +426,44 @@ __global__ void __launch_bounds__(128, KB_ROWS_MINB) kb_rows_kernel(KbIndexView 
         if (lane == 0) KB_DP_STAT(track ? 1 : 0, J->tlen > 256 ? 3 : 2, (int64_t)J->qlen * J->tlen);
         if (track) kb_rows<true>(P, lane, J->qlen, sq, J->tlen, st, J->w, J->zdrop, J->flag, ez, S, &cells);
         else kb_rows<false>(P, lane, J->qlen, sq, J->tlen, st, J->w, J->zdrop, J->flag, ez, S, &cells);
+        kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
+    }
+    if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
+}
+
+// the same for the rectangles kb_rows16 takes: 64 virtual lanes per warp, two cells per DPX instruction
+#ifndef KB_ROWS16_MINB
+#define KB_ROWS16_MINB 5
+#endif
+__global__ void __launch_bounds__(128, KB_ROWS16_MINB) kb_rows16_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *r16_list, uint8_t *scratch,
+                                                          size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
+                                                          unsigned long long *counters)
+{
+    __shared__ uint32_t wmax_ring[4][KB_R16_RING_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
+    S.wmax = wmax_ring[threadIdx.x >> 5];
+    for (int x = lane; x < KB_R16_RING_WORDS; x += 32) S.wmax[x] = 0;
+    __syncwarp();
+    const KbDpConst P = kb_dp_const(ix.p);
+    const long long n_big = (long long)counters[KB_SC_R16_BIG], n = (long long)counters[KB_SC_R16] + n_big;
+    const int64_t job_cap = jobcig_cap / 16;
+    int64_t cells = 0;
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&counters[KB_SC_QR16], 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if ((long long)k >= n) break;
+        KbJob *J = jobs + ((long long)k < n_big ? r16_list[job_cap - 1 - (long long)k] : r16_list[(long long)k - n_big]);
+        const int dir = J->kind == KB_JOB_LEFT ? -1 : 1;
+        const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff + (dir < 0 ? -1 : 0), dir};
+        const KbDirPack st{bt.seq2, bt.nmask, J->tpos + (dir < 0 ? -1 : 0), dir};
+        KbEz ez;
+        const bool track = !(J->flag & KB_EZ_GLOBAL_NO_ZDROP);
+        if (lane == 0) KB_DP_STAT(track ? 1 : 0, J->tlen > 512 ? 3 : 2, (int64_t)J->qlen * J->tlen);
+        if (track) kb_rows16<true>(P, lane, J->qlen, sq, J->tlen, st, J->zdrop, J->flag, ez, S, &cells);
+        else kb_rows16<false>(P, lane, J->qlen, sq, J->tlen, st, J->zdrop, J->flag, ez, S, &cells);
         kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
     }
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
@@ -474,21 +525,31 @@ static int64_t kb_rows_big_thr()
     static const int64_t v = getenv("KAPTIVE_B200_ROWS_BIG") ? atoll(getenv("KAPTIVE_B200_ROWS_BIG")) : 150000;
     return v;
 }
+static int kb_use_rows16()
+{
+    static const int v = !(getenv("KAPTIVE_B200_ROWS16") && getenv("KAPTIVE_B200_ROWS16")[0] == '0');
+    return v;
+}
 void kb_launch_stage_plan(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
                           const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, int64_t job_cap, int32_t *band_list,
-                          int32_t *rows_list, int32_t *slow_list, unsigned long long *counters, cudaStream_t st)
+                          int32_t *rows_list, int32_t *r16_list, int32_t *slow_list, unsigned long long *counters, cudaStream_t st)
 {
     if (n_chains <= 0) return;
+    const KbRowsQueues Q{rows_list, r16_list, job_cap, kb_rows_big_thr(), kb_use_rows16()};
     kb_plan_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, kscratch, (KbPlan *)plans,
-                                                                       (KbJob *)jobs, job_cap, band_list, rows_list, slow_list, counters,
-                                                                       kb_rows_big_thr());
+                                                                       (KbJob *)jobs, job_cap, band_list, Q, slow_list, counters);
 }
-void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, uint8_t *band_scratch,
-                        int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
-                        unsigned long long *counters, cudaStream_t st)
+void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, int32_t *r16_list,
+                        uint8_t *band_scratch, int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig,
+                        int64_t jobcig_cap, unsigned long long *counters, cudaStream_t st)
 {
-    kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, rows_list, band_scratch, kb_band_scratch_bytes(),
-                                                               jobcig, jobcig_cap, counters, kb_rows_big_thr());
+    const KbRowsQueues Q{rows_list, r16_list, jobcig_cap / 16, kb_rows_big_thr(), kb_use_rows16()};
+    kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, Q, band_scratch, kb_band_scratch_bytes(), jobcig,
+                                                               jobcig_cap, counters);
+    int r16_warps = rows_warps / 4 * 4;
+    if (kb_use_rows16())
+        kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, r16_list, rows_scratch, rows_scratch_bytes, jobcig,
+                                                                    jobcig_cap, counters);
     kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, rows_list, rows_scratch, rows_scratch_bytes, jobcig,
                                                                jobcig_cap, counters);
 }
@@ -587,6 +648,88 @@ extern "C" int kb_debug_dp_stats(int64_t *out32, int reset)
         if (cudaMemcpyToSymbol(g_kb_dp_stats, z, sizeof(z)) != cudaSuccess) return -1;
     }
     return 0;
+}
+
+// ------------------------------------------------------------------ DP kernels one by one (diagnostic / parity tests)
+// One warp per job; mode 0 = scratch-memory DP (kb_extd2, the statement closest to the oracle), 1 = kb_rows, 2 = kb_rows16,
+// 3 = certified band pass (kb_global_band).  out: n x 8 = score, max, max_t, max_q, zdropped, n_cigar, ran (0: not eligible), 0.
+__global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const uint8_t *q, const int64_t *qoff, const int32_t *qlen,
+                                                          const uint8_t *t, const int64_t *toff, const int32_t *tlen, const int32_t *flag,
+                                                          const int32_t *w, const int32_t *zdrop, int n, int mode, uint8_t *scratch,
+                                                          size_t scratch_bytes, int32_t *out, uint32_t *cig, int cig_stride)
+{
+    __shared__ uint32_t wmax_ring[4][KB_R16_RING_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, pp.max_sw_cells);
+    S.wmax = wmax_ring[threadIdx.x >> 5];
+    for (int x = lane; x < KB_R16_RING_WORDS; x += 32) S.wmax[x] = 0;
+    __syncwarp();
+    const KbDpConst P = kb_dp_const(pp);
+    for (int64_t k = wg; k < n; k += nw) {
+        const KbPtrSeq sq{q + qoff[k]}, st{t + toff[k]};
+        const int ql = qlen[k], tl = tlen[k], fl = flag[k], ww = w[k], zd = zdrop[k];
+        const bool track = !(fl & KB_EZ_GLOBAL_NO_ZDROP);
+        KbEz ez;
+        ez.max = 0, ez.max_q = ez.max_t = -1, ez.score = KB_NEG_INF, ez.zdropped = 0, ez.n_cigar = 0;
+        int ran = 1;
+        if (mode == 0) kb_extd2<32>(P, lane, ql, sq.p, tl, st.p, ww, zd, fl, ez, S, nullptr);
+        else if (mode == 1) {
+            if (!kb_rows_eligible(P.max_sw_cells, ql, tl, ww, track)) ran = 0;
+            else if (track) kb_rows<true>(P, lane, ql, sq, tl, st, ww, zd, fl, ez, S, nullptr);
+            else kb_rows<false>(P, lane, ql, sq, tl, st, ww, zd, fl, ez, S, nullptr);
+        } else if (mode == 2) {
+            if (!kb_rows16_eligible(P, ql, tl, ww)) ran = 0;
+            else if (track) kb_rows16<true>(P, lane, ql, sq, tl, st, zd, fl, ez, S, nullptr);
+            else kb_rows16<false>(P, lane, ql, sq, tl, st, zd, fl, ez, S, nullptr);
+        } else {
+            if (!kb_band_eligible(P.max_sw_cells, ql, tl, ww, fl)) ran = 0;
+            else ran = kb_global_band(P, lane, ql, sq, tl, st, fl, ez, S, nullptr) ? 1 : 2;  // 2: ran, not certified
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int32_t *o = out + k * 8;
+            o[0] = ez.score, o[1] = ez.max, o[2] = ez.max_t, o[3] = ez.max_q, o[4] = ez.zdropped, o[5] = ez.n_cigar, o[6] = ran, o[7] = 0;
+        }
+        if (ran == 1)
+            for (int i = lane; i < ez.n_cigar && i < cig_stride; i += 32) cig[k * (int64_t)cig_stride + i] = S.ezcig[i];
+        __syncwarp();
+    }
+}
+extern "C" int kb_debug_dp(const kb_params_t *pp, int device, const uint8_t *q, const int64_t *qoff, const int32_t *qlen, const uint8_t *t,
+                           const int64_t *toff, const int32_t *tlen, const int32_t *flag, const int32_t *w, const int32_t *zdrop, int32_t n,
+                           int32_t mode, int32_t *out, uint32_t *cig, int32_t cig_stride)
+{
+    if (!pp || n <= 0 || !out || !cig) return KB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return KB_ERR_CUDA;
+    int64_t qb = 0, tbts = 0;
+    for (int i = 0; i < n; ++i) qb = std::max<int64_t>(qb, qoff[i] + qlen[i]), tbts = std::max<int64_t>(tbts, toff[i] + tlen[i]);
+    const int n_warps = 148 * 4;
+    const size_t sbytes = kb_align_scratch_bytes(pp->max_sw_cells);
+    uint8_t *dq = nullptr, *dt = nullptr, *scr = nullptr;
+    int64_t *dqo = nullptr, *dto = nullptr;
+    int32_t *dql = nullptr, *dtl = nullptr, *dfl = nullptr, *dw = nullptr, *dz = nullptr, *dout = nullptr;
+    uint32_t *dcig = nullptr;
+    int rc = KB_OK;
+    auto up = [&](void **d, const void *h, size_t bytes) {
+        if (cudaMalloc(d, bytes + 16) != cudaSuccess || (h && cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess)) rc = KB_ERR_CUDA;
+    };
+    up((void **)&dq, q, (size_t)qb), up((void **)&dt, t, (size_t)tbts), up((void **)&dqo, qoff, (size_t)n * 8), up((void **)&dto, toff, (size_t)n * 8);
+    up((void **)&dql, qlen, (size_t)n * 4), up((void **)&dtl, tlen, (size_t)n * 4), up((void **)&dfl, flag, (size_t)n * 4);
+    up((void **)&dw, w, (size_t)n * 4), up((void **)&dz, zdrop, (size_t)n * 4);
+    up((void **)&dout, nullptr, (size_t)n * 32), up((void **)&dcig, nullptr, (size_t)n * cig_stride * 4), up((void **)&scr, nullptr, (size_t)n_warps * sbytes);
+    if (rc == KB_OK) {
+        kb_debug_dp_kernel<<<n_warps / 4, 128>>>(*pp, dq, dqo, dql, dt, dto, dtl, dfl, dw, dz, n, mode, scr, sbytes, dout, dcig, cig_stride);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = KB_ERR_CUDA;
+        else if (cudaMemcpy(out, dout, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                 cudaMemcpy(cig, dcig, (size_t)n * cig_stride * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = KB_ERR_CUDA;
+    }
+    (void)cudaGetLastError();
+    for (void *p : {(void *)dq, (void *)dt, (void *)dqo, (void *)dto, (void *)dql, (void *)dtl, (void *)dfl, (void *)dw, (void *)dz, (void *)dout,
+                    (void *)dcig, (void *)scr})
+        if (p) cudaFree(p);
+    return rc;
 }
 
 // ------------------------------------------------------------------ stage dumps for parity tests

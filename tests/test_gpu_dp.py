@@ -1,0 +1,122 @@
+"""The base-level DP kernels one by one (kb_debug_dp): the register-resident forms -- row-stripe wavefront (kb_rows), its packed
+16-bit twin with two cells per DPX instruction (kb_rows16), the certified band pass -- against the scratch-memory DP, which is the
+statement closest to oracle/kb_oracle.c:extd2 and is itself covered against the oracle by the hit-level parity tests.  Bit-exact:
+score, maximum and its cell, z-drop flag, CIGAR."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EXTZ_ONLY, RIGHT, REV_CIGAR, GLOBAL = 1, 2, 4, 8
+NT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _mutate(rng, s, sub, indel):
+    out = []
+    for b in s:
+        r = rng.random()
+        if r < indel / 2:
+            continue
+        if r < indel:
+            out.append(int(rng.integers(0, 4)))
+        out.append(int((b + rng.integers(1, 4)) % 4) if rng.random() < sub else int(b))
+    return np.array(out, np.uint8) if out else np.zeros(1, np.uint8)
+
+
+def make_jobs(seed: int, n: int):
+    rng = np.random.default_rng(seed)
+    q, t, fl, w, zd = [], [], [], [], []
+    for i in range(n):
+        kind = i % 3
+        regime = rng.integers(0, 5)
+        ql = int({0: rng.integers(1, 40), 1: rng.integers(30, 140), 2: rng.integers(100, 400), 3: rng.integers(300, 760),
+                  4: rng.integers(1, 760)}[int(regime)])
+        qs = rng.integers(0, 4, size=ql).astype(np.uint8)
+        sub = float(rng.choice([0.0, 0.02, 0.08, 0.15, 0.3]))
+        ind = float(rng.choice([0.0, 0.005, 0.03]))
+        core = _mutate(rng, qs, sub, ind)
+        if kind == 2:  # global gap fill: target = diverged copy, sometimes with a long indel
+            ts = core
+            if rng.random() < 0.3 and len(ts) > 60:
+                c = int(rng.integers(10, len(ts) - 10))
+                ts = np.concatenate([ts[:c], rng.integers(0, 4, size=int(rng.integers(1, 90))).astype(np.uint8), ts[c:]])
+            ts = ts[:759]
+            f, ww, z = GLOBAL, int(rng.choice([751, 30001])), -1
+        else:  # end extension: the target window is about twice the query (mm_align1), alignment near the diagonal then random
+            tl = max(1, min(2 * ql + int(rng.integers(-3, 4)), 752))
+            tail = rng.integers(0, 4, size=tl).astype(np.uint8)
+            ts = np.concatenate([core, tail])[:tl]
+            if rng.random() < 0.15:  # poor start: z-drop territory
+                ts = rng.integers(0, 4, size=tl).astype(np.uint8)
+            f = (EXTZ_ONLY | RIGHT | REV_CIGAR) if kind == 0 else EXTZ_ONLY
+            ww, z = 751, int(rng.choice([400, 400, 60]))
+        if rng.random() < 0.2:  # ambiguous bases on either side
+            for arr in (qs, ts):
+                k = int(rng.integers(0, 4))
+                if k and len(arr):
+                    arr[rng.integers(0, len(arr), size=k)] = 4
+        q.append(qs), t.append(ts.astype(np.uint8)), fl.append(f), w.append(ww), zd.append(z)
+    return q, t, np.array(fl, np.int32), np.array(w, np.int32), np.array(zd, np.int32)
+
+
+def run(L, params, q, t, fl, w, zd, mode, stride=2048):
+    from kaptive_b200._lib import ptr
+
+    ql = np.array([len(x) for x in q], np.int32)
+    tl = np.array([len(x) for x in t], np.int32)
+    qo = np.concatenate([[0], np.cumsum(ql[:-1])]).astype(np.int64)
+    to = np.concatenate([[0], np.cumsum(tl[:-1])]).astype(np.int64)
+    qq, tt = np.concatenate(q), np.concatenate(t)
+    n = len(q)
+    out = np.zeros((n, 8), np.int32)
+    cig = np.zeros((n, stride), np.uint32)
+    rc = L.kb_debug_dp(C.byref(params), 0, ptr(qq), ptr(qo), ptr(ql), ptr(tt), ptr(to), ptr(tl), ptr(fl), ptr(w), ptr(zd), n, mode, ptr(out),
+                       ptr(cig), stride)
+    assert rc == 0, rc
+    return out, cig
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_register_dp_kernels_equal_the_scratch_dp(seed):
+    from kaptive_b200 import _lib
+
+    L = _lib.load()
+    P = _lib.default_params()
+    q, t, fl, w, zd = make_jobs(seed, 900)
+    ref, rcig = run(L, P, q, t, fl, w, zd, 0)
+    n_ran = {}
+    for mode, name in ((1, "rows"), (2, "rows16"), (3, "band")):
+        got, gcig = run(L, P, q, t, fl, w, zd, mode)
+        ran = got[:, 6] == 1
+        n_ran[name] = int(ran.sum())
+        for i in np.nonzero(ran)[0]:
+            desc = (name, int(i), len(q[i]), len(t[i]), int(fl[i]), int(w[i]), int(zd[i]))
+            if fl[i] & GLOBAL:
+                assert got[i, 0] == ref[i, 0], (desc, "score", got[i].tolist(), ref[i].tolist())
+            else:
+                assert got[i, 1:5].tolist() == ref[i, 1:5].tolist(), (desc, "max / zdrop", got[i].tolist(), ref[i].tolist())
+                if not ref[i, 4]:
+                    assert got[i, 0] == ref[i, 0], (desc, "score", got[i].tolist(), ref[i].tolist())
+            assert got[i, 5] == ref[i, 5], (desc, "n_cigar", got[i].tolist(), ref[i].tolist())
+            nc = int(ref[i, 5])
+            assert np.array_equal(gcig[i, :nc], rcig[i, :nc]), (desc, "cigar")
+    assert n_ran["rows"] > 800 and n_ran["rows16"] > 600 and n_ran["band"] > 50, n_ran
+
+
+def test_rows16_range_limits_fall_back():
+    """Rectangles the packed kernel must refuse: a band of the spec that binds, a target shorter than the 64-lane ramp pays for."""
+    from kaptive_b200 import _lib
+
+    L = _lib.load()
+    P = _lib.default_params()
+    rng = np.random.default_rng(3)
+    q = [rng.integers(0, 4, size=900).astype(np.uint8), rng.integers(0, 4, size=50).astype(np.uint8)]
+    t = [rng.integers(0, 4, size=900).astype(np.uint8), rng.integers(0, 4, size=20).astype(np.uint8)]
+    fl, w, zd = np.array([EXTZ_ONLY, EXTZ_ONLY], np.int32), np.array([751, 751], np.int32), np.array([400, 400], np.int32)
+    got, _ = run(L, P, q, t, fl, w, zd, 2)
+    assert got[:, 6].tolist() == [0, 0]
