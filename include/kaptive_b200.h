@@ -158,7 +158,7 @@ int kb_debug_dp_stats(int64_t *out32, int reset);
 
 /* diagnostic / parity tests: runs n independent base-level DP problems (nt4 codes 0..4, concatenated) through ONE of the DP
  * kernels: mode 0 scratch-memory DP (the form closest to oracle/kb_oracle.c:extd2), 1 row-stripe wavefront, 2 packed 16-bit
- * row-stripe wavefront, 3 certified 64-diagonal band pass.  flag: KB_EZ_* bits (1 extension only, 2 right-aligned gaps,
+ * row-stripe wavefront (job alone), 3 certified 64-diagonal band pass, 4 packed 16-bit wavefront with jobs 2i and 2i + 1 as a pair.  flag: KB_EZ_* bits (1 extension only, 2 right-aligned gaps,
  * 4 reversed CIGAR, 8 global without z-drop).  out: n x 8 int32 = score, max, max_t, max_q, zdropped, n_cigar, ran (0: the
  * kernel is not eligible for this problem, 2: band pass not certified), 0; cig: n x cig_stride BAM-encoded operations. */
 int kb_debug_dp(const kb_params_t *params, int device, const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t,

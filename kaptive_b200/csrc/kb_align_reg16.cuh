@@ -1,30 +1,39 @@
 // kb_align_reg16.cuh -- the row-stripe wavefront of kb_align_reg.cuh with TWO cells per instruction (device only).
 //
 // Blackwell's DPX instructions work on packed signed halfwords (VIADDMNMX.S16x2, VIMNMX3.S16x2, VIMNMX.S16x2 with two
-// predicate outputs, VIADD.16x2); kb_rows16 keeps every DP value of kb_rows as an x8-domain score with its priority tag
-// in 16 bits and lets one warp act as 64 virtual lanes: the low halfword of every register belongs to virtual lane
-// `lane`, the high halfword to virtual lane `lane + 32`.  A tile is 64 stripes of up to 8 columns (512 columns); virtual
-// lane v computes row s - v of its stripe at step s, so the high half simply runs 32 steps behind the low half, and
-// lane 0's high half takes its left neighbour from lane 31's low half (a rotating shuffle).  Recurrences, tie rules,
-// per-anti-diagonal maxima / z-drop rule and traceback bytes are those of kb_rows (the spec is oracle/kb_oracle.c:extd2).
+// predicate outputs, VIADD.16x2).  kb_rows16 keeps every DP value of kb_rows as an x8-domain score with its priority tag in
+// 16 bits and runs TWO DP JOBS in one warp: the low halfword of every register belongs to job A, the high halfword to job B.
+// Geometry, step schedule and neighbour shuffles are exactly those of kb_rows (tiles of 256 columns, lane = a stripe of up
+// to 8 columns, row s - lane at step s), so a pair costs one pass of kb_rows over the larger of the two rectangles;
+// the kernel sorts its jobs by size and pairs neighbours, which keeps that maximum close to both.  Recurrences, tie rules,
+// per-anti-diagonal maxima / z-drop rule and traceback bytes are those of kb_rows (the spec is oracle/kb_oracle.c:extd2);
+// the two jobs may differ in every parameter (lengths, band, z-drop, left / right tie rule).
+// (A first version made one job 64 virtual lanes wide instead: correct, but the 63-step ramp and the 64-column rounding ate
+// the gain -- 109 thread instructions per useful cell pair; profiles/r2_summary.md.)
 //
 // Range.  A score of the rectangle lies in [-(gap(qlen) + gap(tlen) + q2 + e2 + q + e), a * min(qlen, tlen)]; times 8 plus
 // the tag this must fit a signed halfword, which kb_rows16_eligible checks (genes are ~1 kb: with the default scoring
-// any rectangle with qlen + tlen <= 3900 qualifies).  No value is ever a "minus infinity" sentinel: the states that
+// any rectangle with qlen + tlen <= 3600 qualifies).  No value is ever a "minus infinity" sentinel: the states that
 // kb_rows initialises with KB_NEG8 start here at "gap opened from the boundary cell", which the first real cell
-// reproduces anyway (same value, same tag), so nothing can wrap.  Only unbanded rectangles are taken (|t - j| <= w for
-// every cell); the banded ones and the few over the range stay with kb_rows.
+// reproduces anyway (same value, same tag), so nothing can wrap.  Cells the band of the spec excludes (|t - j| > w) are set to
+// KB_NEG16, a value below every real one of an eligible rectangle that is re-imposed on every such cell, so it cannot decay
+// towards the wrap either; rectangles over the range stay with kb_rows.
 //
 // Substitution scores: the QUERY base of a row gives a word of four score bytes (against target A, C, G, T; all equal for
-// an ambiguous query base), one word per half, built once per step; every column keeps a byte-permute selector made
-// from its two target bases, so one PRMT yields both halves' sign-extended scores.  A tile that holds an ambiguous TARGET
-// base (0.01 % of the bases) runs a variant of the row that patches those columns.
+// an ambiguous query base), one word per job, built once per step; every column keeps a byte-permute selector made
+// from the two jobs' target bases, so one PRMT yields both halves' sign-extended scores.  A tile that holds an ambiguous
+// TARGET base (0.01 % of the bases) runs a variant of the row that patches those columns.
 #pragma once
 #ifdef __CUDACC__
 
-#define KB_R16_RING 1024                      // anti-diagonals in the per-warp ring of kb_rows16 (TRACK)
-#define KB_R16_RING_WORDS (KB_R16_RING + 8)   // + 8 alias words, folded back by drain()
-#define KB_R16_MIN_TLEN 33                    // below this the 32-lane kernel's shorter ramp wins
+#define KB_R16_RING_WORDS (2 * KB_RING_WORDS)  // one ring of kb_rows' size per job of the pair
+// per-warp shared memory of kb_rows16: the two rings, a 5-entry table of query score words per job, and the two query segments
+// as nt4 bytes in DP order with 32 bytes of padding on either side (a lane reads row s - lane for -31 <= s - lane < qlen + 31)
+#define KB_R16_QMAX 2048
+#define KB_R16_LUT_OFF KB_R16_RING_WORDS
+#define KB_R16_SQ_OFF (KB_R16_RING_WORDS + 16)
+#define KB_R16_SQ_WORDS ((KB_R16_QMAX + 64) / 4)
+#define KB_R16_SMEM_WORDS (KB_R16_SQ_OFF + 2 * KB_R16_SQ_WORDS)
 
 __device__ __forceinline__ uint32_t kb_add2(uint32_t a, uint32_t b)
 {
@@ -36,34 +45,38 @@ __device__ __forceinline__ uint32_t kb_pack2(int lo, int hi) { return ((uint32_t
 __device__ __forceinline__ int kb_lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int kb_hi16(uint32_t v) { return (int)v >> 16; }
 
-KB_HD bool kb_rows16_eligible(const KbDpConst &P, int qlen, int tlen, int w)
+KB_HD bool kb_rows16_eligible(const KbDpConst &P, int qlen, int tlen, int w, bool track)
 {
-    if (qlen <= 0 || tlen < KB_R16_MIN_TLEN || qlen > 4000 || tlen > 4000) return false;
-    if (tlen - 1 > w || qlen - 1 > w) return false;  // a band of the spec would bind: kb_rows masks it
-    const int64_t tiles = (tlen + 511) / 512;
-    if (tiles * (qlen + 63) * 512 > P.max_sw_cells || (int64_t)qlen * tlen > P.max_sw_cells) return false;
+    if (qlen <= 0 || tlen <= 0 || qlen > KB_R16_QMAX || tlen > 4000) return false;
+    const int dlen = tlen > qlen ? tlen - qlen : qlen - tlen;
+    if (w < 2 || (!track && dlen >= w)) return false;  // as kb_rows_eligible: a global alignment whose end cell the band excludes
+    // each job of a pair gets half of the warp's traceback scratch; a pair's tiles and steps are those of its larger member
+    // (kb_rows16_pair_fits); two jobs that do not fit together are run one after the other, each with the scratch to itself
+    const int64_t tiles = (tlen + 255) / 256;
+    if (tiles * (qlen + 31) * 256 > P.max_sw_cells || (int64_t)qlen * tlen > P.max_sw_cells) return false;
     const int lo = kb_gapcost2(P, qlen + 1) + kb_gapcost2(P, tlen + 1) + P.q + P.e + P.q2 + P.e2 + P.b + P.sc_ambi + 8;
     const int hi = P.a * (qlen < tlen ? qlen : tlen) + 8;
-    return lo < 4000 && hi < 4000 && P.a <= 15 && P.b <= 15 && P.sc_ambi <= 15;
+    return lo < 3700 && hi < 4000 && P.a <= 15 && P.b <= 15 && P.sc_ambi <= 15;  // lo: real values stay above KB_NEG16 + gap costs
 }
 
-struct KbC16 {                      // kb_c8's constants, the same value in both halves
+struct KbC16 {                      // kb_c8's constants: low half for job A (tie rule rbA), high half for job B (rbB)
     uint32_t oe1, oe2, of1, of2;    // open + first extension with the state's tag
     uint32_t nx1, nx2;              // minus the extension cost
     uint32_t th1, th2;              // flag thresholds relative to H8, as ">=": -8 q + (rb ? 0 : 8)
-    int rb;
 };
-__device__ __forceinline__ KbC16 kb_c16(const KbDpConst &P, int rb)
+__device__ __forceinline__ KbC16 kb_c16(const KbDpConst &P, int rbA, int rbB)
 {
     KbC16 c;
-    const int tE1 = rb ? 4 : 6, tF1 = 5, tE2 = rb ? 6 : 4, tF2 = rb ? 7 : 3;
-    auto both = [](int v) { return kb_pack2(v, v); };
-    c.rb = rb;
-    c.oe1 = both(-8 * (P.q + P.e) + tE1), c.of1 = both(-8 * (P.q + P.e) + tF1);
-    c.oe2 = both(-8 * (P.q2 + P.e2) + tE2), c.of2 = both(-8 * (P.q2 + P.e2) + tF2);
-    c.nx1 = both(-8 * P.e), c.nx2 = both(-8 * P.e2);
+    auto tE1 = [](int rb) { return rb ? 4 : 6; };
+    auto tE2 = [](int rb) { return rb ? 6 : 4; };
+    auto tF2 = [](int rb) { return rb ? 7 : 3; };
+    const int tF1 = 5;
+    c.oe1 = kb_pack2(-8 * (P.q + P.e) + tE1(rbA), -8 * (P.q + P.e) + tE1(rbB)), c.of1 = kb_pack2(-8 * (P.q + P.e) + tF1, -8 * (P.q + P.e) + tF1);
+    c.oe2 = kb_pack2(-8 * (P.q2 + P.e2) + tE2(rbA), -8 * (P.q2 + P.e2) + tE2(rbB));
+    c.of2 = kb_pack2(-8 * (P.q2 + P.e2) + tF2(rbA), -8 * (P.q2 + P.e2) + tF2(rbB));
+    c.nx1 = kb_pack2(-8 * P.e, -8 * P.e), c.nx2 = kb_pack2(-8 * P.e2, -8 * P.e2);
     // kb_cell8 tests "state > H8 + (-8 q + (rb ? -1 : 7))"; the packed compare answers ">=", so the threshold is one higher
-    c.th1 = both(-8 * P.q + (rb ? 0 : 8)), c.th2 = both(-8 * P.q2 + (rb ? 0 : 8));
+    c.th1 = kb_pack2(-8 * P.q + (rbA ? 0 : 8), -8 * P.q + (rbB ? 0 : 8)), c.th2 = kb_pack2(-8 * P.q2 + (rbA ? 0 : 8), -8 * P.q2 + (rbB ? 0 : 8));
     return c;
 }
 // score word of a query base: byte k = 8 * score(k, cq) + diagonal tag against target k = A, C, G, T
@@ -109,58 +122,83 @@ __device__ __forceinline__ uint32_t kb_cell16(const KbC16 &c, uint32_t hu, uint3
     return z;
 }
 
-template <bool TN, bool TRACK, int M>
-__device__ __forceinline__ void kb_rows16_cell(const KbC16 &c, uint32_t qlo, uint32_t qhi, const uint32_t (&sel)[8], uint32_t nbits, uint32_t sNw,
-                                               uint32_t &hu, uint32_t &e1, uint32_t &e2, uint32_t &hd, uint32_t (&Hc)[8], uint32_t (&F1)[8],
-                                               uint32_t (&F2)[8], uint32_t (&tb)[4], unsigned ring_lo, unsigned ring_hi, int32_t ckey_lo,
-                                               int32_t ckey_hi, int nvm_lo, int nvm_hi)
-{
-    uint32_t s = (uint32_t)kb_prmt(qlo, qhi, sel[M]);
-    if (TN) {  // ambiguous target base in this column of either half: the score is -sc_ambi whatever the query base
-        const uint32_t m = ((nbits >> M) & 1u ? 0x0000ffffu : 0u) | ((nbits >> (8 + M)) & 1u ? 0xffff0000u : 0u);
-        s = (s & ~m) | (sNw & m);
-    }
-    uint32_t d;
-    const uint32_t hl = Hc[M];
-    const uint32_t z = kb_cell16(c, hu, e1, e2, hl, F1[M], F2[M], hd, s, d);
-    hd = hl, Hc[M] = z, hu = z;
-    tb[M >> 1] += d << (8 * (M & 1));  // d < 128 per half: two columns share a halfword
-    if (TRACK) {
-        // key = (H + 2^19) << 12 | (4095 - t), as in kb_rows; slot M is M words past the half's slot-0 anti-diagonal
-        const int zl = kb_lo16(z), zh = kb_hi16(z);
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 k;\n\t"
-                     "setp.lt.s32 p, %3, %4;\n\tmad.lo.s32 k, %0, 512, %1;\n\t"
-                     "@p red.shared.max.u32 [%2+%5], k;\n\t}" ::"r"(zl), "r"(ckey_lo - M), "r"(ring_lo), "n"(M), "r"(nvm_lo), "n"(4 * M)
-                     : "memory");
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 k;\n\t"
-                     "setp.lt.s32 p, %3, %4;\n\tmad.lo.s32 k, %0, 512, %1;\n\t"
-                     "@p red.shared.max.u32 [%2+%5], k;\n\t}" ::"r"(zh), "r"(ckey_hi - M), "r"(ring_hi), "n"(M), "r"(nvm_hi), "n"(4 * M)
-                     : "memory");
-    }
-}
-template <bool TN, bool TRACK>
-__device__ __forceinline__ void kb_rows16_body(const KbC16 &c, int kact, uint32_t qlo, uint32_t qhi, const uint32_t (&sel)[8], uint32_t nbits,
-                                               uint32_t sNw, uint32_t &hu, uint32_t &e1, uint32_t &e2, uint32_t &hd, uint32_t (&Hc)[8],
-                                               uint32_t (&F1)[8], uint32_t (&F2)[8], uint32_t (&tb)[4], unsigned ring_lo, unsigned ring_hi,
-                                               int32_t ckey_lo, int32_t ckey_hi, int nvm_lo, int nvm_hi)
+// value of a cell the band of the spec excludes: far below every real value of an eligible rectangle, far above -32768 - gap costs
+#define KB_NEG16 (-30000)
+
+// One row of a job pair: the first kact of 8 cells, straight line with an exit after every cell (slot m holds column
+// t0 + m); ONE copy of the code serves every stripe width, which keeps the hot loop of the kernel inside the instruction cache
+// (a copy per width ran 2.4 x slower).  SLOW adds what few rows need: ambiguous target bases (nbits), cells outside a band.
+template <bool SLOW, bool TRACK, int KACT>
+__device__ __forceinline__ void kb_rows16_row(const KbC16 &c, uint32_t qlo, uint32_t qhi, const uint32_t (&sel)[8], uint32_t nbits,
+                                              uint32_t sNw, uint32_t &hu, uint32_t &e1, uint32_t &e2, uint32_t hd, uint32_t (&Hc)[8],
+                                              uint32_t (&F1)[8], uint32_t (&F2)[8], uint32_t (&tb)[4], unsigned ring_lo, unsigned ring_hi,
+                                              uint32_t tinv, int nv_lo, int nv_hi, int w_lo, int w_hi, int d0)
 {
     tb[0] = tb[1] = tb[2] = tb[3] = 0;
-#define KB_RC(M) \
-    kb_rows16_cell<TN, TRACK, M>(c, qlo, qhi, sel, nbits, sNw, hu, e1, e2, hd, Hc, F1, F2, tb, ring_lo, ring_hi, ckey_lo, ckey_hi, nvm_lo, nvm_hi)
-    switch (kact) {  // a stripe of kact < 8 columns lives in the LAST kact slots
-    case 8: KB_RC(0);
-    case 7: KB_RC(1);
-    case 6: KB_RC(2);
-    case 5: KB_RC(3);
-    case 4: KB_RC(4);
-    case 3: KB_RC(5);
-    case 2: KB_RC(6);
-    default: KB_RC(7);
+#pragma unroll
+    for (int M = 0; M < KACT; ++M) {
+        uint32_t s = (uint32_t)kb_prmt(qlo, qhi, sel[M]);
+        if (SLOW) {  // ambiguous target base in this column of either job: the score is -sc_ambi whatever the query base
+            const uint32_t m = ((nbits >> M) & 1u ? 0x0000ffffu : 0u) | ((nbits >> (8 + M)) & 1u ? 0xffff0000u : 0u);
+            s = (s & ~m) | (sNw & m);
+        }
+        uint32_t d;
+        const uint32_t hl = Hc[M];
+        uint32_t z = kb_cell16(c, hu, e1, e2, hl, F1[M], F2[M], hd, s, d);
+        bool okl = true, okh = true;
+        if (SLOW) {
+            okl = (unsigned)(d0 + M + w_lo) <= (unsigned)(2 * w_lo), okh = (unsigned)(d0 + M + w_hi) <= (unsigned)(2 * w_hi);
+            const uint32_t m = (okl ? 0u : 0x0000ffffu) | (okh ? 0u : 0xffff0000u);
+            if (m) {
+                const uint32_t neg = kb_pack2(KB_NEG16, KB_NEG16) & m;
+                z = (z & ~m) | neg, e1 = (e1 & ~m) | neg, e2 = (e2 & ~m) | neg, F1[M] = (F1[M] & ~m) | neg, F2[M] = (F2[M] & ~m) | neg, d &= ~m;
+            }
+        }
+        hd = hl, Hc[M] = z, hu = z;
+        tb[M >> 1] += d << (8 * (M & 1));  // d < 128 per half: two columns share a halfword
+        if (TRACK) {
+            // key = (H8 ^ 0x8000) << 16 | (65535 - t): unsigned order = (H, lowest t); slot M is M words past slot 0's anti-diagonal in the
+            // job's own ring; a key of 0 (job not on a real row, padded column, cell outside the band) leaves the ring unchanged
+            const uint32_t zx = z ^ 0x80008000u, tm = tinv - M;
+            uint32_t kl = (uint32_t)kb_prmt(zx, tm, 0x1054), kh = (uint32_t)kb_prmt(zx, tm, 0x3254);
+            kl = (M < nv_lo && okl) ? kl : 0u, kh = (M < nv_hi && okh) ? kh : 0u;  // okl / okh are constants in the fast form
+            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring_lo + 4 * M), "r"(kl) : "memory");
+            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ring_hi + 4 * M), "r"(kh) : "memory");
+        }
     }
-#undef KB_RC
+}
+// dispatch on the stripe width: the fast form has a straight-line copy per width (no exits, no register shuffling at joins), the
+// rarely used slow form one copy with an exit after every cell
+template <bool SLOW, bool TRACK>
+__device__ __forceinline__ void kb_rows16_rowk(const KbC16 &c, int kact, uint32_t qlo, uint32_t qhi, const uint32_t (&sel)[8], uint32_t nbits,
+                                               uint32_t sNw, uint32_t &hu, uint32_t &e1, uint32_t &e2, uint32_t hd, uint32_t (&Hc)[8],
+                                               uint32_t (&F1)[8], uint32_t (&F2)[8], uint32_t (&tb)[4], unsigned ring_lo, unsigned ring_hi,
+                                               uint32_t tinv, int nv_lo, int nv_hi, int w_lo, int w_hi, int d0)
+{
+#define KB_RK(K) \
+    kb_rows16_row<SLOW, TRACK, K>(c, qlo, qhi, sel, nbits, sNw, hu, e1, e2, hd, Hc, F1, F2, tb, ring_lo, ring_hi, tinv, nv_lo, nv_hi, w_lo, w_hi, d0)
+    switch (kact) {
+    case 8: KB_RK(8); break;
+    case 7: KB_RK(7); break;
+    case 6: KB_RK(6); break;
+    case 5: KB_RK(5); break;
+    case 4: KB_RK(4); break;
+    case 3: KB_RK(3); break;
+    case 2: KB_RK(2); break;
+    default: KB_RK(1); break;
+    }
+#undef KB_RK
 }
 
 // [mm2:ksw2.h:ksw_apply_zdrop] over the per-anti-diagonal keys rmax[0, n_diag), in order: see kb_rows for the derivation.
+// KEY16: keys of kb_rows16, (H8 ^ 0x8000) << 16 | (65535 - t); otherwise keys of kb_rows, (H + 2^19) << 12 | (4095 - t).
+template <bool KEY16>
+__device__ __forceinline__ void kb_key_decode(uint32_t key, int32_t &h, int32_t &t)
+{
+    if (KEY16) h = (int32_t)(short)((key >> 16) ^ 0x8000u) >> 3, t = 65535 - (int32_t)(key & 0xffffu);
+    else h = (int32_t)(key >> 12) - (1 << 19), t = 4095 - (int32_t)(key & 4095u);
+}
+template <bool KEY16>
 static __device__ __forceinline__ void kb_zdrop_scan(const KbDpConst &P, int lane, const uint32_t *rmax, int n_diag, int zdrop, KbEz &z_)
 {
     const int chunk = (n_diag + 31) >> 5, lo = lane * chunk, hi = lo + chunk < n_diag ? lo + chunk : n_diag;
@@ -168,8 +206,9 @@ static __device__ __forceinline__ void kb_zdrop_scan(const KbDpConst &P, int lan
     for (int r = lo; r < hi; ++r) {
         const uint32_t key = rmax[r];
         if (key == 0) continue;
-        const int32_t h = (int32_t)(key >> 12) - (1 << 19);
-        if (h > lmx) lmx = h, lr = r, lt = 4095 - (int32_t)(key & 4095u);
+        int32_t h, t;
+        kb_key_decode<KEY16>(key, h, t);
+        if (h > lmx) lmx = h, lr = r, lt = t;
     }
     int smx = lmx, sr = lr, st = lt;
 #pragma unroll
@@ -186,7 +225,8 @@ static __device__ __forceinline__ void kb_zdrop_scan(const KbDpConst &P, int lan
         const uint32_t key = rmax[r];
         bool brk = key == 0;  // empty anti-diagonal (band excludes it): the spec stops here
         if (!brk) {
-            const int32_t max_H = (int32_t)(key >> 12) - (1 << 19), max_t = 4095 - (int32_t)(key & 4095u);
+            int32_t max_H, max_t;
+            kb_key_decode<KEY16>(key, max_H, max_t);
             if (max_H > mx) mx = max_H, mt = max_t, mq = r - max_t;
             else if (max_t >= mt && r - max_t >= mq) {
                 const int tl = max_t - mt, ql = (r - max_t) - mq, l = tl > ql ? tl - ql : ql - tl;
@@ -206,168 +246,231 @@ static __device__ __forceinline__ void kb_zdrop_scan(const KbDpConst &P, int lan
     z_.max = __shfl_sync(0xffffffffu, mx, owner), z_.max_t = __shfl_sync(0xffffffffu, mt, owner), z_.max_q = __shfl_sync(0xffffffffu, mq, owner);
 }
 
-// S.wmax must point at KB_R16_RING_WORDS zeroed words of shared memory when TRACK.
-template <bool TRACK, class SQ, class ST>
-static __device__ __noinline__ void kb_rows16(const KbDpConst P, int lane, int qlen, const SQ qs, int tlen, const ST ts, int zdrop, int flag,
-                                              KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
+// columns per lane of tile `tile` for a pair whose targets are tlenA / tlenB long (0: absent): the wider need of the two
+__device__ __forceinline__ int kb_pair_kact(int tlenA, int tlenB, int tile)
 {
-    const int rb = (flag & KB_EZ_RIGHT) ? 1 : 0;
-    const KbC16 c = kb_c16(P, rb);
-    const int tag_d = rb ? 3 : 7;
-    const int ntile = (tlen + 511) >> 9, nstep = qlen + 63, n_diag = qlen + tlen - 1;
-    const int klast = (tlen - ((ntile - 1) << 9) + 63) >> 6;  // columns per virtual lane in the last tile
-    const size_t tile_bytes = (size_t)nstep * 512;
-    uint8_t *tb = S.tb;
-    int32_t *edge = S.dp;                                  // [parity][3][KB_DP_MAXLEN]
-    uint32_t *rmax = reinterpret_cast<uint32_t *>(S.off);  // per anti-diagonal key (TRACK)
-    const unsigned ring = TRACK ? (unsigned)__cvta_generic_to_shared(S.wmax) : 0u;
-    const uint32_t sNw = kb_pack2(-8 * P.sc_ambi + tag_d, -8 * P.sc_ambi + tag_d);
-    const int of1 = kb_lo16(c.of1), of2 = kb_lo16(c.of2), oe1 = kb_lo16(c.oe1), oe2 = kb_lo16(c.oe2);
-    if (TRACK) {
-        for (int r = lane; r < n_diag; r += 32) rmax[r] = 0;
+    const int tl = tlenA > tlenB ? tlenA : tlenB, ntile = (tl + 255) >> 8;
+    return tile + 1 < ntile ? 8 : (tl - ((ntile - 1) << 8) + 31) >> 5;
+}
+KB_HD bool kb_rows16_pair_fits(const KbDpConst &P, int qlenA, int tlenA, int qlenB, int tlenB)
+{
+    const int ql = qlenA > qlenB ? qlenA : qlenB, tl = tlenA > tlenB ? tlenA : tlenB;
+    return (int64_t)((tl + 255) >> 8) * (ql + 31) * 256 <= P.max_sw_cells / 2;
+}
+
+// One job of a pair, as the DP pass sees it.  An absent job B has qlen = tlen = 0.
+template <class SQ, class ST>
+struct KbPairJob {
+    int qlen, tlen, w, zdrop, flag;
+    SQ qs;
+    ST ts;
+};
+struct KbPairOut {  // what the DP pass leaves for kb_rows16_finish
+    int32_t scoreA, scoreB;
+    int nstep;
+};
+
+// The DP pass of a pair: traceback bytes of job A in S.tb[0, max_sw_cells / 2), of job B in the second half; per-anti-diagonal
+// keys in S.off (A) and S.off + 2 * KB_DP_MAXLEN (B) when TRACK.  S.wmax: KB_R16_RING_WORDS zeroed words of shared memory.
+template <bool TRACK, class SQ, class ST>
+static __device__ __noinline__ void kb_rows16_dp(const KbDpConst P, int lane, const KbPairJob<SQ, ST> A, const KbPairJob<SQ, ST> B, KbPairOut &out,
+                                                 const KbAlignScratch S)
+{
+    const int rbA = (A.flag & KB_EZ_RIGHT) ? 1 : 0, rbB = (B.flag & KB_EZ_RIGHT) ? 1 : 0;
+    const KbC16 c = kb_c16(P, rbA, rbB);
+    const int tagA = rbA ? 3 : 7, tagB = rbB ? 3 : 7;
+    const int qmax = A.qlen > B.qlen ? A.qlen : B.qlen, tmax = A.tlen > B.tlen ? A.tlen : B.tlen;
+    const int ntile = (tmax + 255) >> 8, nstep = qmax + 31;
+    const int ntA = (A.tlen + 255) >> 8, ntB = (B.tlen + 255) >> 8;
+    const int ndA = A.qlen + A.tlen - 1, ndB = B.qlen + B.tlen - 1;
+    const bool bandedA = A.tlen - 1 > A.w || A.qlen - 1 > A.w, bandedB = B.qlen > 0 && (B.tlen - 1 > B.w || B.qlen - 1 > B.w);
+    const size_t tile_bytes = (size_t)nstep * 256;
+    uint8_t *tbA = S.tb, *tbB = S.tb + (P.max_sw_cells >> 1);
+    uint32_t *edge = reinterpret_cast<uint32_t *>(S.dp);   // [parity][3][KB_DP_MAXLEN], packed like the registers
+    uint32_t *rmaxA = reinterpret_cast<uint32_t *>(S.off), *rmaxB = rmaxA + 2 * KB_DP_MAXLEN;
+    uint32_t *wmA = S.wmax, *wmB = S.wmax + KB_RING_WORDS;
+    const unsigned ringA = TRACK ? (unsigned)__cvta_generic_to_shared(wmA) : 0u, ringB = ringA + 4 * KB_RING_WORDS;
+    const uint32_t sNw = kb_pack2(-8 * P.sc_ambi + tagA, -8 * P.sc_ambi + tagB);
+    const int of1 = kb_lo16(c.of1);
+    const uint32_t dOF1 = c.of1, dOF2 = c.of2, dOE1 = c.oe1, dOE2 = c.oe2;
+    out.scoreA = out.scoreB = KB_NEG_INF, out.nstep = nstep;
+    (void)of1;
+    // the two query segments as bytes in shared memory (row j at byte 32 + j), and each job's table of score words by query base
+    const unsigned sm_base = (unsigned)__cvta_generic_to_shared(S.wmax);
+    const unsigned sqA = sm_base + 4 * KB_R16_SQ_OFF + 32, sqB = sqA + 4 * KB_R16_SQ_WORDS, lutA = sm_base + 4 * KB_R16_LUT_OFF, lutB = lutA + 32;
+    {
+        uint8_t *ba = reinterpret_cast<uint8_t *>(S.wmax + KB_R16_SQ_OFF) + 32, *bb = ba + 4 * KB_R16_SQ_WORDS;
+        for (int x = lane; x < A.qlen; x += 32) ba[x] = (uint8_t)A.qs(x);
+        for (int x = lane; x < B.qlen; x += 32) bb[x] = (uint8_t)B.qs(x);
+        if (lane < 5) S.wmax[KB_R16_LUT_OFF + lane] = kb_qrow16(P, tagA, lane), S.wmax[KB_R16_LUT_OFF + 8 + lane] = kb_qrow16(P, tagB, lane);
         __syncwarp();
     }
-    auto drain = [&](int r_lo) {  // fold the ring entries of anti-diagonals [r_lo, r_lo + KB_R16_RING) into rmax[]
+    auto lds8 = [](unsigned a) {
+        unsigned v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    };
+    auto lds32 = [](unsigned a) {
+        unsigned v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    };
+    if (TRACK) {
+        for (int r = lane; r < ndA; r += 32) rmaxA[r] = 0;
+        for (int r = lane; r < ndB; r += 32) rmaxB[r] = 0;
         __syncwarp();
-        if (lane < 8) {  // alias words first: word RING + x stands for word x
-            const uint32_t a = S.wmax[KB_R16_RING + lane];
+    }
+    auto drain1 = [&](uint32_t *wm, uint32_t *rmax, int n_diag, int r_lo) {  // as kb_rows: ring entries [r_lo, r_lo + 512) into rmax[]
+        if (lane < 8) {  // alias words first: word 512 + x stands for word x
+            const uint32_t a = wm[512 + lane];
             if (a) {
-                S.wmax[KB_R16_RING + lane] = 0;
-                if (a > S.wmax[lane]) S.wmax[lane] = a;
+                wm[512 + lane] = 0;
+                if (a > wm[lane]) wm[lane] = a;
             }
         }
         __syncwarp();
-        for (int r = r_lo + lane; r < r_lo + KB_R16_RING; r += 32) {
+        for (int r = r_lo + lane; r < r_lo + 512; r += 32) {
             if (r < 0 || r >= n_diag) continue;
-            const uint32_t v = S.wmax[r & (KB_R16_RING - 1)];
+            const uint32_t v = wm[r & 511];
             if (v) {
-                S.wmax[r & (KB_R16_RING - 1)] = 0;
+                wm[r & 511] = 0;
                 if (v > rmax[r]) rmax[r] = v;
             }
         }
+    };
+    auto drain = [&](int r_lo) {
+        __syncwarp();
+        drain1(wmA, rmaxA, ndA, r_lo);
+        drain1(wmB, rmaxB, ndB, r_lo);
         __syncwarp();
     };
-    int32_t score = KB_NEG_INF;
     for (int tile = 0; tile < ntile; ++tile) {
-        const bool spill = tile + 1 < ntile;  // then the tile is full width: its last column is slot 7 of lane 31's high half
-        const int kact = spill ? 8 : klast, koff = 8 - kact;
-        const int T0 = tile << 9;
-        const int t0_lo = T0 + lane * kact, t0_hi = t0_lo + 32 * kact;     // first column of the two stripes
-        const int t0s_lo = t0_lo - koff, t0s_hi = t0_hi - koff;            // slot m holds column t0s + m (m >= koff)
-        const int32_t *ein = edge + (size_t)((tile & 1) ^ 1) * 3 * KB_DP_MAXLEN;
-        int32_t *eout = edge + (size_t)(tile & 1) * 3 * KB_DP_MAXLEN;
+        const bool spill = tile + 1 < ntile;  // then the tile is full width and its last column is lane 31's slot 7
+        const int kact = spill ? 8 : (tmax - ((ntile - 1) << 8) + 31) >> 5;
+        const int T0 = tile << 8, t0 = T0 + lane * kact;  // slot m holds column t0 + m
+        const bool onA = tile < ntA, onB = tile < ntB;      // a job whose target ends in an earlier tile sits this one out
+        const uint32_t *ein = edge + (size_t)((tile & 1) ^ 1) * 3 * KB_DP_MAXLEN;
+        uint32_t *eout = edge + (size_t)(tile & 1) * 3 * KB_DP_MAXLEN;
         uint32_t Hc[8], F1[8], F2[8], sel[8];
         uint32_t nbits = 0;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int tl = t0s_lo + m, th = t0s_hi + m;
-            const int cl = (m >= koff && tl < tlen) ? ts(tl) : 0, ch = (m >= koff && th < tlen) ? ts(th) : 0;
-            sel[m] = kb_sel16(cl, ch);
-            if (cl > 3) nbits |= 1u << m;
-            if (ch > 3) nbits |= 1u << (8 + m);
-            // virtual row j = -1 of the low half (the high half is initialised when its first row comes up)
-            const int h0 = -8 * kb_gapcost2(P, tl + 1);
-            Hc[m] = kb_pack2(h0, 0), F1[m] = kb_pack2(h0 + of1, 0), F2[m] = kb_pack2(h0 + of2, 0);
+            const int t = t0 + m;
+            const int ca = (m < kact && t < A.tlen) ? A.ts(t) : 0, cb = (m < kact && t < B.tlen) ? B.ts(t) : 0;
+            sel[m] = kb_sel16(ca, cb);
+            if (ca > 3) nbits |= 1u << m;
+            if (cb > 3) nbits |= 1u << (8 + m);
+            const int h0 = -8 * kb_gapcost2(P, t + 1);  // virtual row j = -1
+            Hc[m] = kb_pack2(h0, h0), F1[m] = kb_add2(Hc[m], dOF1), F2[m] = kb_add2(Hc[m], dOF2);
         }
-        const bool tile_has_n = __any_sync(0xffffffffu, nbits != 0);
-        int nval_lo = tlen - t0_lo, nval_hi = tlen - t0_hi;
-        nval_lo = nval_lo < 0 ? 0 : (nval_lo > kact ? kact : nval_lo), nval_hi = nval_hi < 0 ? 0 : (nval_hi > kact ? kact : nval_hi);
-        const int nvm_lo = nval_lo > 0 ? koff + nval_lo : 0, nvm_hi = nval_hi > 0 ? koff + nval_hi : 0;  // slots below nvm hold real columns
-        // what a virtual lane offers to the next one: (H, E1, E2) of its last column in the row it has just finished
-        uint32_t oh = kb_pack2(-8 * kb_gapcost2(P, t0_lo + kact), -8 * kb_gapcost2(P, t0_hi + kact)), oe1p = 0, oe2p = 0;
-        uint32_t dg = kb_pack2(T0 == 0 ? 0 : -8 * kb_gapcost2(P, T0), 0);  // lane 0 low: H(T0 - 1, -1); everything else: set by the shuffles
-        uint8_t *tbt = tb + (size_t)tile * tile_bytes + lane * 8;
-        // the step at which the cell (tlen - 1, qlen - 1) is finished, and who owns it (last tile only)
-        const int cc_fin = tlen - 1 - T0, v_fin = cc_fin / kact, ms_fin = koff + cc_fin % kact, s_fin = qlen - 1 + v_fin;
-        int cq_lo_next = qs(lane == 0 ? 0 : qlen - 1), cq_hi_next = qs(qlen - 1);
+        const bool tile_slow = __any_sync(0xffffffffu, nbits != 0);  // an ambiguous target base: every row of the tile takes the slow form
+        int nvA = A.tlen - t0, nvB = B.tlen - t0;  // real columns of the stripe in either job
+        nvA = nvA < 0 ? 0 : (nvA > kact ? kact : nvA), nvB = nvB < 0 ? 0 : (nvB > kact ? kact : nvB);
+        // what the lane offers to lane + 1: (H, E1, E2) of its last column in the row it has just finished
+        const int hoff = -8 * kb_gapcost2(P, t0 + kact);
+        uint32_t oh = kb_pack2(hoff, hoff), oe1p = 0, oe2p = 0;
+        const int dg0 = T0 == 0 ? 0 : -8 * kb_gapcost2(P, T0);
+        uint32_t dg = kb_pack2(dg0, dg0);  // lane 0: H(T0 - 1, -1); other lanes: set by the first shuffle
+        uint8_t *tbt = tbA + (size_t)tile * tile_bytes + lane * 8;
+        const size_t b_off = (size_t)(P.max_sw_cells >> 1);
+        // the step at which the cell (tlen - 1, qlen - 1) of a job is finished, its lane and slot (the job's last tile only)
+        const int ccA = A.tlen - 1 - T0, ccB = B.tlen - 1 - T0;
+        const int sfA = (tile == ntA - 1) ? A.qlen - 1 + ccA / kact : -1, sfB = (tile == ntB - 1) ? B.qlen - 1 + ccB / kact : -1;
+        // score words of the row a lane is on, fetched one step ahead (bytes outside [0, qlen) are never used: the job is not active there)
+        uint32_t qlo_next = lds32(lutA + 4 * (lds8(sqA - lane) & 7u)), qhi_next = lds32(lutB + 4 * (lds8(sqB - lane) & 7u));
         for (int s = 0; s < nstep; ++s) {
-            const int cq_lo = cq_lo_next, cq_hi = cq_hi_next;
-            const int j_lo = s - lane, j_hi = j_lo - 32;
-            {
-                int jn = j_lo + 1;
-                jn = jn < 0 ? 0 : (jn >= qlen ? qlen - 1 : jn);
-                cq_lo_next = qs(jn);
-                jn = j_hi + 1;
-                jn = jn < 0 ? 0 : (jn >= qlen ? qlen - 1 : jn);
-                cq_hi_next = qs(jn);
+            const uint32_t qlo = qlo_next, qhi = qhi_next;
+            const int j = s - lane;
+            qlo_next = lds32(lutA + 4 * (lds8(sqA + j + 1) & 7u)), qhi_next = lds32(lutB + 4 * (lds8(sqB + j + 1) & 7u));
+            uint32_t uh = __shfl_up_sync(0xffffffffu, oh, 1), ue1 = __shfl_up_sync(0xffffffffu, oe1p, 1), ue2 = __shfl_up_sync(0xffffffffu, oe2p, 1);
+            const bool actA = onA && (unsigned)j < (unsigned)A.qlen, actB = onB && (unsigned)j < (unsigned)B.qlen;
+            if (lane == 0 && (actA || actB)) {  // the rectangle's left edge, or the previous tile's last column
+                if (T0 == 0) {
+                    const int bh = -8 * kb_gapcost2(P, j + 1);
+                    uh = kb_pack2(bh, bh), ue1 = kb_add2(uh, dOE1), ue2 = kb_add2(uh, dOE2);
+                } else uh = kb_ld_u32(ein + j), ue1 = kb_ld_u32(ein + KB_DP_MAXLEN + j), ue2 = kb_ld_u32(ein + 2 * KB_DP_MAXLEN + j);
             }
-            const int src = (lane + 31) & 31;
-            uint32_t uh = __shfl_sync(0xffffffffu, oh, src), ue1 = __shfl_sync(0xffffffffu, oe1p, src), ue2 = __shfl_sync(0xffffffffu, oe2p, src);
-            const bool act_lo = (unsigned)j_lo < (unsigned)qlen, act_hi = (unsigned)j_hi < (unsigned)qlen;
-            if (lane == 0) {  // low half: the rectangle's left edge or the previous tile's last column; high half: lane 31's low half
-                int bh = 0, b1 = 0, b2 = 0;
-                if (act_lo) {
-                    if (T0 == 0) bh = -8 * kb_gapcost2(P, j_lo + 1), b1 = bh + oe1, b2 = bh + oe2;
-                    else bh = kb_ld_s32(ein + j_lo), b1 = kb_ld_s32(ein + KB_DP_MAXLEN + j_lo), b2 = kb_ld_s32(ein + 2 * KB_DP_MAXLEN + j_lo);
-                }
-                uh = (uint32_t)kb_prmt((uint32_t)bh, uh, 0x5410), ue1 = (uint32_t)kb_prmt((uint32_t)b1, ue1, 0x5410);
-                ue2 = (uint32_t)kb_prmt((uint32_t)b2, ue2, 0x5410);
+            // band of the spec: a lane whose stripe touches |t - j| > w in this row (either job)
+            const int d0 = t0 - j;  // diagonal of slot 0
+            bool slow = tile_slow;
+            if (bandedA || bandedB) {
+                const bool edge_lane = (bandedA && actA && (d0 < -A.w || d0 + kact - 1 > A.w)) || (bandedB && actB && (d0 < -B.w || d0 + kact - 1 > B.w));
+                slow = slow || __any_sync(0xffffffffu, edge_lane);
             }
-            if (j_hi == 0) {  // the high half's stripe starts now: virtual row j = -1
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const int h0 = -8 * kb_gapcost2(P, t0s_hi + m + 1);
-                    Hc[m] = (uint32_t)kb_prmt(Hc[m], (uint32_t)h0, 0x5410);
-                    F1[m] = (uint32_t)kb_prmt(F1[m], (uint32_t)(h0 + of1), 0x5410);
-                    F2[m] = (uint32_t)kb_prmt(F2[m], (uint32_t)(h0 + of2), 0x5410);
-                }
-            }
-            if (act_lo || act_hi) {
-                const uint32_t qlo = kb_qrow16(P, tag_d, cq_lo), qhi = kb_qrow16(P, tag_d, cq_hi);
-                uint32_t hu = uh, e1 = ue1, e2 = ue2, hd = dg;
+            if (actA || actB) {
+                uint32_t hu = uh, e1 = ue1, e2 = ue2;
                 uint32_t tbw[4];
-                const unsigned rs_lo = ring + (((unsigned)(t0s_lo + j_lo) & (KB_R16_RING - 1)) << 2);
-                const unsigned rs_hi = ring + (((unsigned)(t0s_hi + j_hi) & (KB_R16_RING - 1)) << 2);
-                const int nv_lo = act_lo ? nvm_lo : 0, nv_hi = act_hi ? nvm_hi : 0;
-                if (tile_has_n)
-                    kb_rows16_body<true, TRACK>(c, kact, qlo, qhi, sel, nbits, sNw, hu, e1, e2, hd, Hc, F1, F2, tbw, rs_lo, rs_hi,
-                                                KB_ROWS_KEY_BIAS - t0s_lo, KB_ROWS_KEY_BIAS - t0s_hi, nv_lo, nv_hi);
+                const unsigned ro = ((unsigned)(t0 + j) & 511u) << 2;
+                int nv_lo = actA ? nvA : 0, nv_hi = actB ? nvB : 0;
+                asm volatile("" : "+r"(nv_lo), "+r"(nv_hi));  // two plain registers: otherwise every cell re-derives them from their conditions
+                if (slow)
+                    kb_rows16_rowk<true, TRACK>(c, kact, qlo, qhi, sel, nbits, sNw, hu, e1, e2, dg, Hc, F1, F2, tbw, ringA + ro, ringB + ro,
+                                               0xffffu - (uint32_t)t0, nv_lo, nv_hi, A.w, B.w, d0);
                 else
-                    kb_rows16_body<false, TRACK>(c, kact, qlo, qhi, sel, nbits, sNw, hu, e1, e2, hd, Hc, F1, F2, tbw, rs_lo, rs_hi,
-                                                 KB_ROWS_KEY_BIAS - t0s_lo, KB_ROWS_KEY_BIAS - t0s_hi, nv_lo, nv_hi);
-                // a half that is not on a real row keeps its offer (the row -1 value its neighbour needs as a diagonal)
-                const uint32_t keep = act_lo ? (act_hi ? 0x3210u : 0x7610u) : 0x3254u;
-                oh = (uint32_t)kb_prmt(hu, oh, keep), oe1p = (uint32_t)kb_prmt(e1, oe1p, keep), oe2p = (uint32_t)kb_prmt(e2, oe2p, keep);
-                // a virtual lane's slot is 8 bytes wide whatever kact is: low half at [lane * 8], high half 256 bytes on
-                if (act_lo) {
+                    kb_rows16_rowk<false, TRACK>(c, kact, qlo, qhi, sel, nbits, sNw, hu, e1, e2, dg, Hc, F1, F2, tbw, ringA + ro, ringB + ro,
+                                                0xffffu - (uint32_t)t0, nv_lo, nv_hi, A.w, B.w, d0);
+                oh = hu, oe1p = e1, oe2p = e2;
+                // a lane's slot is 8 bytes wide whatever kact is; job A's bytes are the low halves, job B's the high halves
+                if (actA) {
                     const uint32_t w0 = (uint32_t)kb_prmt(tbw[0], tbw[1], 0x5410), w1 = (uint32_t)kb_prmt(tbw[2], tbw[3], 0x5410);
                     asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(tbt)), "r"(w0), "r"(w1) : "memory");
                 }
-                if (act_hi) {
+                if (actB) {
                     const uint32_t w0 = (uint32_t)kb_prmt(tbw[0], tbw[1], 0x7632), w1 = (uint32_t)kb_prmt(tbw[2], tbw[3], 0x7632);
-                    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(tbt + 256)), "r"(w0), "r"(w1) : "memory");
-                    if (spill && lane == 31)
-                        kb_st_s32(eout + j_hi, kb_hi16(oh)), kb_st_s32(eout + KB_DP_MAXLEN + j_hi, kb_hi16(oe1p)),
-                            kb_st_s32(eout + 2 * KB_DP_MAXLEN + j_hi, kb_hi16(oe2p));
+                    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(tbt + b_off)), "r"(w0), "r"(w1) : "memory");
                 }
+                if (spill && lane == 31) kb_st_u32(eout + j, oh), kb_st_u32(eout + KB_DP_MAXLEN + j, oe1p), kb_st_u32(eout + 2 * KB_DP_MAXLEN + j, oe2p);
             }
             dg = uh;
-            tbt += 512;
-            if (!spill && s == s_fin) {  // H(tlen - 1, qlen - 1) has just been computed by virtual lane v_fin
+            tbt += 256;
+            if (s == sfA || s == sfB) {  // H(tlen - 1, qlen - 1) of a job has just been computed
+                const int cc = s == sfA ? ccA : ccB, ms = cc % kact;
                 uint32_t hv = Hc[0];
 #pragma unroll
                 for (int m = 1; m < 8; ++m)
-                    if (m == ms_fin) hv = Hc[m];
-                hv = __shfl_sync(0xffffffffu, hv, v_fin & 31);
-                score = (v_fin >> 5 ? kb_hi16(hv) : kb_lo16(hv)) >> 3;
+                    if (m == ms) hv = Hc[m];
+                hv = __shfl_sync(0xffffffffu, hv, cc / kact);
+                if (s == sfA) out.scoreA = kb_lo16(hv) >> 3;
+                if (s == sfB) {  // (both can finish in the same step)
+                    const int msb = ccB % kact;
+                    uint32_t hb = Hc[0];
+#pragma unroll
+                    for (int m = 1; m < 8; ++m)
+                        if (m == msb) hb = Hc[m];
+                    hb = __shfl_sync(0xffffffffu, hb, ccB / kact);
+                    out.scoreB = kb_hi16(hb) >> 3;
+                }
             }
-            if (TRACK && (s & 511) == 511) drain(T0 + s - 543);
+            if (TRACK && (s & 255) == 255) drain(T0 + s - 287);
         }
-        if (TRACK) drain(T0 + nstep - 544), drain(T0 + nstep + 480);
+        if (TRACK) drain(T0 + nstep - 288), drain(T0 + nstep + 224);
         __syncwarp();  // spilled column visible to lane 0 of the next tile
     }
+}
+
+// z-drop rule + traceback of ONE job of the pair (which = 0: A, 1: B) into S.ezcig / ez.
+template <bool TRACK, class SQ, class ST>
+static __device__ __noinline__ void kb_rows16_finish(const KbDpConst P, int lane, const KbPairJob<SQ, ST> J, int which, int tlen_other,
+                                                     const KbPairOut out, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)
+{
+    const int rb = (J.flag & KB_EZ_RIGHT) ? 1 : 0;
+    const int n_diag = J.qlen + J.tlen - 1;
+    const uint8_t *tb = S.tb + (which ? (size_t)(P.max_sw_cells >> 1) : 0);
+    const uint32_t *rmax = reinterpret_cast<const uint32_t *>(S.off) + (which ? 2 * KB_DP_MAXLEN : 0);
+    const size_t tile_bytes = (size_t)out.nstep * 256;
+    const int tlA = which ? tlen_other : J.tlen, tlB = which ? J.tlen : tlen_other;
     KbEz z_;
     z_.max = 0, z_.max_q = z_.max_t = -1, z_.score = KB_NEG_INF, z_.zdropped = 0, z_.n_cigar = 0;
-    if (TRACK) kb_zdrop_scan(P, lane, rmax, n_diag, zdrop, z_);
-    if (!z_.zdropped) z_.score = score;
-    if (cell_counter && lane == 0) *cell_counter += (int64_t)qlen * tlen;
+    if (TRACK && !(J.flag & KB_EZ_GLOBAL_NO_ZDROP)) kb_zdrop_scan<true>(P, lane, rmax, n_diag, J.zdrop, z_);
+    if (!z_.zdropped) z_.score = which ? out.scoreB : out.scoreA;
+    if (cell_counter && lane == 0) *cell_counter += (int64_t)J.qlen * J.tlen;
     int i = -1, j = -1;
-    if (!z_.zdropped && !(flag & KB_EZ_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+    if (!z_.zdropped && !(J.flag & KB_EZ_EXTZ_ONLY)) i = J.tlen - 1, j = J.qlen - 1;
     else if (z_.max_t >= 0 && z_.max_q >= 0) i = z_.max_t, j = z_.max_q;
-    z_.n_cigar = kb_backtrack_warp(lane, i, j, rb, flag, S.ezcig, [&](int ii, int jj) -> uint32_t {
-        const int tile = ii >> 9, cc = ii & 511, kk = tile + 1 < ntile ? 8 : klast;
-        const int v = cc / kk;
-        return (uint32_t)kb_ld_u8(tb + (size_t)tile * tile_bytes + (size_t)(jj + v) * 512 + v * 8 + (8 - kk) + (cc - v * kk));
+    z_.n_cigar = kb_backtrack_warp(lane, i, j, rb, J.flag, S.ezcig, [&](int ii, int jj) -> uint32_t {
+        const int tile = ii >> 8, cc = ii & 255, kk = kb_pair_kact(tlA, tlB, tile);
+        const int l = cc / kk;
+        return (uint32_t)kb_ld_u8(tb + (size_t)tile * tile_bytes + (size_t)(jj + l) * 256 + l * 8 + (cc - l * kk));
     });
     ez = z_;
 }

@@ -270,16 +270,18 @@ void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChain
 #define KB_SC_QR16 37
 struct KbRowsQueues {
     int32_t *rows_list, *r16_list;
+    uint32_t *r16_key;  // size class of every job in r16_list: the list is sorted by it (descending) and neighbours are paired
     int64_t job_cap, big_thr;
     int use16;
 };
 __device__ __forceinline__ void kb_rows_enqueue(const KbRowsQueues &Q, const KbDpConst &P, unsigned long long *counters, const KbJob &J, int32_t jid)
 {
-    const bool big = Q.big_thr > 0 && (int64_t)J.qlen * J.tlen >= Q.big_thr;
-    if (Q.use16 && kb_rows16_eligible(P, J.qlen, J.tlen, J.w)) {
-        if (big) Q.r16_list[Q.job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_R16_BIG], 1ull)] = jid;
-        else Q.r16_list[atomicAdd(&counters[KB_SC_R16], 1ull)] = jid;
-    } else if (big) Q.rows_list[Q.job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_ROWS_BIG], 1ull)] = jid;
+    const bool track = !(J.flag & KB_EZ_GLOBAL_NO_ZDROP);
+    if (Q.use16 && kb_rows16_eligible(P, J.qlen, J.tlen, J.w, track)) {
+        const unsigned long long k = atomicAdd(&counters[KB_SC_R16], 1ull);
+        Q.r16_list[k] = jid;
+        Q.r16_key[k] = (track ? 1u << 28 : 0u) | (uint32_t)J.qlen << 14 | (uint32_t)J.tlen;  // > 0; unused slots hold 0
+    } else if (Q.big_thr > 0 && (int64_t)J.qlen * J.tlen >= Q.big_thr) Q.rows_list[Q.job_cap - 1 - (int64_t)atomicAdd(&counters[KB_SC_ROWS_BIG], 1ull)] = jid;
     else Q.rows_list[atomicAdd(&counters[KB_SC_ROWS], 1ull)] = jid;
 }
 __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
@@ -431,40 +433,60 @@ __global__ void __launch_bounds__(128, KB_ROWS_MINB) kb_rows_kernel(KbIndexView 
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
 }
 
-// the same for the rectangles kb_rows16 takes: 64 virtual lanes per warp, two cells per DPX instruction
+// the rectangles kb_rows16 takes: two jobs per warp (neighbours of the size-sorted list), two cells per DPX instruction
 #ifndef KB_ROWS16_MINB
-#define KB_ROWS16_MINB 5
+#define KB_ROWS16_MINB 4  // 128 registers, 16 warps per SM: at 96 the selector and state arrays spill into the hot loop (measured 260 vs 234 ms align)
 #endif
-__global__ void __launch_bounds__(128, KB_ROWS16_MINB) kb_rows16_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *r16_list, uint8_t *scratch,
+__global__ void __launch_bounds__(128, KB_ROWS16_MINB) kb_rows16_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *r16_sorted, uint8_t *scratch,
                                                           size_t scratch_bytes, uint32_t *jobcig, int64_t jobcig_cap,
                                                           unsigned long long *counters)
 {
-    __shared__ uint32_t wmax_ring[4][KB_R16_RING_WORDS];
+    __shared__ uint32_t wmax_ring[4][KB_R16_SMEM_WORDS];
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, ix.p.max_sw_cells);
     S.wmax = wmax_ring[threadIdx.x >> 5];
-    for (int x = lane; x < KB_R16_RING_WORDS; x += 32) S.wmax[x] = 0;
+    for (int x = lane; x < KB_R16_SMEM_WORDS; x += 32) S.wmax[x] = 0;
     __syncwarp();
     const KbDpConst P = kb_dp_const(ix.p);
-    const long long n_big = (long long)counters[KB_SC_R16_BIG], n = (long long)counters[KB_SC_R16] + n_big;
-    const int64_t job_cap = jobcig_cap / 16;
+    const long long n = (long long)counters[KB_SC_R16], n_pairs = (n + 1) >> 1;
     int64_t cells = 0;
+    typedef KbPairJob<KbDirBytes, KbDirPack> PJ;
+    auto view = [&](const KbJob *J) {
+        const int dir = J->kind == KB_JOB_LEFT ? -1 : 1;
+        return PJ{J->qlen, J->tlen, J->w, J->zdrop, J->flag,
+                  KbDirBytes{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff + (dir < 0 ? -1 : 0), dir},
+                  KbDirPack{bt.seq2, bt.nmask, J->tpos + (dir < 0 ? -1 : 0), dir}};
+    };
+    const PJ none{0, 0, 0, -1, KB_EZ_GLOBAL_NO_ZDROP, KbDirBytes{ix.gseq_fwd, 1}, KbDirPack{bt.seq2, bt.nmask, 0, 1}};
+    auto run = [&](KbJob *Ja, KbJob *Jb) {  // Jb may be null
+        const PJ A = view(Ja), B = Jb ? view(Jb) : none;
+        const bool track = !(A.flag & KB_EZ_GLOBAL_NO_ZDROP) || (Jb && !(B.flag & KB_EZ_GLOBAL_NO_ZDROP));
+        KbPairOut out;
+        KbEz ez;
+        if (track) kb_rows16_dp<true>(P, lane, A, B, out, S);
+        else kb_rows16_dp<false>(P, lane, A, B, out, S);
+        if (track) kb_rows16_finish<true>(P, lane, A, 0, B.tlen, out, ez, S, &cells);
+        else kb_rows16_finish<false>(P, lane, A, 0, B.tlen, out, ez, S, &cells);
+        kb_job_finish(lane, Ja, ez, S.ezcig, jobcig, jobcig_cap, counters);
+        if (Jb) {
+            if (track) kb_rows16_finish<true>(P, lane, B, 1, A.tlen, out, ez, S, &cells);
+            else kb_rows16_finish<false>(P, lane, B, 1, A.tlen, out, ez, S, &cells);
+            kb_job_finish(lane, Jb, ez, S.ezcig, jobcig, jobcig_cap, counters);
+        }
+    };
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(&counters[KB_SC_QR16], 1ull);
         k = __shfl_sync(0xffffffffu, k, 0);
-        if ((long long)k >= n) break;
-        KbJob *J = jobs + ((long long)k < n_big ? r16_list[job_cap - 1 - (long long)k] : r16_list[(long long)k - n_big]);
-        const int dir = J->kind == KB_JOB_LEFT ? -1 : 1;
-        const KbDirBytes sq{(J->qrev ? ix.gseq_rev : ix.gseq_fwd) + J->qbase + J->qoff + (dir < 0 ? -1 : 0), dir};
-        const KbDirPack st{bt.seq2, bt.nmask, J->tpos + (dir < 0 ? -1 : 0), dir};
-        KbEz ez;
-        const bool track = !(J->flag & KB_EZ_GLOBAL_NO_ZDROP);
-        if (lane == 0) KB_DP_STAT(track ? 1 : 0, J->tlen > 512 ? 3 : 2, (int64_t)J->qlen * J->tlen);
-        if (track) kb_rows16<true>(P, lane, J->qlen, sq, J->tlen, st, J->zdrop, J->flag, ez, S, &cells);
-        else kb_rows16<false>(P, lane, J->qlen, sq, J->tlen, st, J->zdrop, J->flag, ez, S, &cells);
-        kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
+        if ((long long)k >= n_pairs) break;
+        KbJob *Ja = jobs + r16_sorted[2 * k], *Jb = (long long)(2 * k + 1) < n ? jobs + r16_sorted[2 * k + 1] : nullptr;
+        if (lane == 0) {  // path 4: the packed 16-bit wavefront
+            KB_DP_STAT((Ja->flag & KB_EZ_GLOBAL_NO_ZDROP) ? 0 : 1, 4, (int64_t)Ja->qlen * Ja->tlen);
+            if (Jb) KB_DP_STAT((Jb->flag & KB_EZ_GLOBAL_NO_ZDROP) ? 0 : 1, 4, (int64_t)Jb->qlen * Jb->tlen);
+        }
+        if (Jb && !kb_rows16_pair_fits(P, Ja->qlen, Ja->tlen, Jb->qlen, Jb->tlen)) run(Ja, nullptr), run(Jb, nullptr);
+        else run(Ja, Jb);
     }
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
 }
@@ -532,24 +554,37 @@ static int kb_use_rows16()
 }
 void kb_launch_stage_plan(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
                           const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, int64_t job_cap, int32_t *band_list,
-                          int32_t *rows_list, int32_t *r16_list, int32_t *slow_list, unsigned long long *counters, cudaStream_t st)
+                          int32_t *rows_list, int32_t *r16_list, uint32_t *r16_key, int32_t *slow_list, unsigned long long *counters,
+                          cudaStream_t st)
 {
     if (n_chains <= 0) return;
-    const KbRowsQueues Q{rows_list, r16_list, job_cap, kb_rows_big_thr(), kb_use_rows16()};
+    const KbRowsQueues Q{rows_list, r16_list, r16_key, job_cap, kb_rows_big_thr(), kb_use_rows16()};
     kb_plan_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, kscratch, (KbPlan *)plans,
                                                                        (KbJob *)jobs, job_cap, band_list, Q, slow_list, counters);
 }
-void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, int32_t *r16_list,
-                        uint8_t *band_scratch, int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig,
-                        int64_t jobcig_cap, unsigned long long *counters, cudaStream_t st)
+size_t kb_r16_sort_temp_bytes(int64_t n)
 {
-    const KbRowsQueues Q{rows_list, r16_list, jobcig_cap / 16, kb_rows_big_thr(), kb_use_rows16()};
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                              (int32_t *)nullptr, n, 0, 29);
+    return b;
+}
+// r16_key / r16_list: job_cap entries (unused ones hold key 0); r16_key2 / r16_list2: the sorted copies; sort_tmp: kb_r16_sort_temp_bytes
+void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, int32_t *r16_list,
+                        uint32_t *r16_key, int32_t *r16_list2, uint32_t *r16_key2, void *sort_tmp, size_t sort_tmp_bytes, uint8_t *band_scratch,
+                        int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
+                        unsigned long long *counters, cudaStream_t st)
+{
+    const int64_t job_cap = jobcig_cap / 16;
+    const KbRowsQueues Q{rows_list, r16_list, r16_key, job_cap, kb_rows_big_thr(), kb_use_rows16()};
     kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, Q, band_scratch, kb_band_scratch_bytes(), jobcig,
                                                                jobcig_cap, counters);
     int r16_warps = rows_warps / 4 * 4;
-    if (kb_use_rows16())
-        kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, r16_list, rows_scratch, rows_scratch_bytes, jobcig,
+    if (kb_use_rows16()) {
+        cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sort_tmp_bytes, r16_key, r16_key2, r16_list, r16_list2, job_cap, 0, 29, st);
+        kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, r16_list2, rows_scratch, rows_scratch_bytes, jobcig,
                                                                     jobcig_cap, counters);
+    }
     kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, rows_list, rows_scratch, rows_scratch_bytes, jobcig,
                                                                jobcig_cap, counters);
 }
@@ -658,12 +693,12 @@ __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const 
                                                           const int32_t *w, const int32_t *zdrop, int n, int mode, uint8_t *scratch,
                                                           size_t scratch_bytes, int32_t *out, uint32_t *cig, int cig_stride)
 {
-    __shared__ uint32_t wmax_ring[4][KB_R16_RING_WORDS];
+    __shared__ uint32_t wmax_ring[4][KB_R16_SMEM_WORDS];
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
     KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, pp.max_sw_cells);
     S.wmax = wmax_ring[threadIdx.x >> 5];
-    for (int x = lane; x < KB_R16_RING_WORDS; x += 32) S.wmax[x] = 0;
+    for (int x = lane; x < KB_R16_SMEM_WORDS; x += 32) S.wmax[x] = 0;
     __syncwarp();
     const KbDpConst P = kb_dp_const(pp);
     for (int64_t k = wg; k < n; k += nw) {
@@ -678,10 +713,27 @@ __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const 
             if (!kb_rows_eligible(P.max_sw_cells, ql, tl, ww, track)) ran = 0;
             else if (track) kb_rows<true>(P, lane, ql, sq, tl, st, ww, zd, fl, ez, S, nullptr);
             else kb_rows<false>(P, lane, ql, sq, tl, st, ww, zd, fl, ez, S, nullptr);
-        } else if (mode == 2) {
-            if (!kb_rows16_eligible(P, ql, tl, ww)) ran = 0;
-            else if (track) kb_rows16<true>(P, lane, ql, sq, tl, st, zd, fl, ez, S, nullptr);
-            else kb_rows16<false>(P, lane, ql, sq, tl, st, zd, fl, ez, S, nullptr);
+        } else if (mode == 2 || mode == 4) {
+            // mode 2: the job alone in the low half; mode 4: paired with job k ^ 1 (this job in the low half when k is even)
+            typedef KbPairJob<KbPtrSeq, KbPtrSeq> PJ;
+            const int64_t ko = (mode == 4 && (k ^ 1) < n) ? (k ^ 1) : -1;
+            const PJ me{ql, tl, ww, zd, fl, sq, st};
+            PJ other{0, 0, 0, -1, KB_EZ_GLOBAL_NO_ZDROP, sq, st};
+            bool pair = false;
+            if (ko >= 0) {
+                const PJ o{qlen[ko], tlen[ko], w[ko], zdrop[ko], flag[ko], KbPtrSeq{q + qoff[ko]}, KbPtrSeq{t + toff[ko]}};
+                pair = kb_rows16_eligible(P, o.qlen, o.tlen, o.w, !(o.flag & KB_EZ_GLOBAL_NO_ZDROP)) && kb_rows16_pair_fits(P, ql, tl, o.qlen, o.tlen);
+                if (pair) other = o;
+            }
+            if (!kb_rows16_eligible(P, ql, tl, ww, track) || (mode == 4 && !pair)) ran = 0;
+            else {
+                const bool me_hi = pair && (k & 1);
+                const PJ &A = me_hi ? other : me, &B = me_hi ? me : other;
+                const bool tr = !(A.flag & KB_EZ_GLOBAL_NO_ZDROP) || (pair && !(B.flag & KB_EZ_GLOBAL_NO_ZDROP));
+                KbPairOut po;
+                if (tr) kb_rows16_dp<true>(P, lane, A, B, po, S), kb_rows16_finish<true>(P, lane, me, me_hi ? 1 : 0, other.tlen, po, ez, S, nullptr);
+                else kb_rows16_dp<false>(P, lane, A, B, po, S), kb_rows16_finish<false>(P, lane, me, me_hi ? 1 : 0, other.tlen, po, ez, S, nullptr);
+            }
         } else {
             if (!kb_band_eligible(P.max_sw_cells, ql, tl, ww, fl)) ran = 0;
             else ran = kb_global_band(P, lane, ql, sq, tl, st, fl, ez, S, nullptr) ? 1 : 2;  // 2: ran, not certified
