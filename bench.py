@@ -9,8 +9,10 @@ one resident 18.8 GB packed buffer.  `--db k --n-asm 1000` gives configs[1].
 
   value      : assemblies/s with the 2-bit packed batch already resident in HBM (wall clock between
                device synchronisations, max over ranks; device-event time reported beside it)
-  e2e        : the same metric through the host-buffer C-ABI call (kb_map_assemblies): pinned ASCII
-               contigs -> H2D -> pack -> map -> D2H of the hit arrays, every step
+  e2e        : the same metric through the host-buffer C-ABI call (kb_map_assemblies_packed): contigs
+               packed 2 bit + N mask by the library's FASTA ingest (kb_fasta_ingest_pack, host threads) in
+               pinned memory -> H2D -> map -> D2H of the hit arrays, every step; `e2e.ascii` is the same
+               call fed with pinned ASCII (kb_map_assemblies: H2D of 1 B per base + the device pack kernel)
   roofline   : the seeding scan kernel, algorithmic bytes / CUDA-event time vs the measured HBM peak
   cpu_baseline / --impl reference : the CPU oracle (a port of the reference's mapper algorithm; the
                reference's own mapper `rammappy` is a closed Rust wheel that is not installable here)
@@ -51,7 +53,8 @@ def parse_args():
     ap.add_argument("--n-loci", type=int, default=150)
     ap.add_argument("--genes-per-locus", type=int, default=20)
     ap.add_argument("--n-core", type=int, default=4)
-    ap.add_argument("--e2e-asm", type=int, default=1000, help="assemblies per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-asm", type=int, default=2000, help="assemblies per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-ascii-asm", type=int, default=1000, help="assemblies per end-to-end step of the ASCII variant (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 4 x cores, 64..96)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -310,14 +313,48 @@ def run_ours(a):
     batch = mapper.AssemblyBatch(wl.ascii.data_ptr(), wl.contig_off, wl.contig_len, wl.asm_contig_start, device=local)
     packed_bytes = batch.packed_bytes
 
-    # end-to-end inputs: pinned host ASCII of the first e2e_asm assemblies
+    # end-to-end inputs: the first e2e_asm assemblies as FASTA bytes -> the library's packed ingest into pinned host buffers
+    from kaptive_b200 import ingest
+
     ne = min(a.e2e_asm, a.n_asm)
+    na = min(a.e2e_ascii_asm, ne)
     nc_e = int(wl.asm_contig_start[ne])
-    host_ascii = torch.empty(ne * a.asm_len, dtype=torch.uint8).pin_memory()
-    host_ascii.copy_(wl.ascii[: ne * a.asm_len])
-    e_off = np.ascontiguousarray(wl.contig_off[:nc_e])
+    nc_a = int(wl.asm_contig_start[na])
     e_len = np.ascontiguousarray(wl.contig_len[:nc_e])
     e_acs = np.ascontiguousarray(wl.asm_contig_start[: ne + 1])
+    fasta = []
+    for i0 in range(0, ne, 64):  # host copies in pieces: FASTA text of one assembly = one record per contig, one line per record
+        i1 = min(ne, i0 + 64)
+        blk = wl.ascii[i0 * a.asm_len : i1 * a.asm_len].cpu().numpy()
+        for i in range(i0, i1):
+            c0, c1 = int(wl.asm_contig_start[i]), int(wl.asm_contig_start[i + 1])
+            parts = []
+            for c in range(c0, c1):
+                o = int(wl.contig_off[c]) - i0 * a.asm_len
+                parts += [b">c%d\n" % (c - c0), blk[o : o + int(wl.contig_len[c])].tobytes(), b"\n"]
+            fasta.append(b"".join(parts))
+    soff = np.zeros(max(nc_e, 1), np.int64)
+    storage = C.c_int64(0)
+    check(load().kb_packed_layout(ptr(e_len), nc_e, ptr(soff), C.byref(storage)))
+    pin_seq2 = torch.empty(storage.value // 16, dtype=torch.int32).pin_memory()
+    pin_mask = torch.empty(storage.value // 32, dtype=torch.int32).pin_memory()
+    ingest_threads = min(os.cpu_count() or 1, 32)
+    t0 = time.perf_counter()
+    pb = ingest.ingest_fasta_packed(fasta, threads=ingest_threads, out=(pin_seq2.numpy().view(np.uint32), pin_mask.numpy().view(np.uint32)), want_names=False)
+    ingest_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pb = ingest.ingest_fasta_packed(fasta, threads=ingest_threads, out=(pin_seq2.numpy().view(np.uint32), pin_mask.numpy().view(np.uint32)), want_names=False)
+    ingest_s = min(ingest_s, time.perf_counter() - t0)
+    assert np.array_equal(pb.contig_len, e_len) and np.array_equal(pb.asm_contig_start, e_acs)
+    fasta_bytes = sum(len(f) for f in fasta)
+    del fasta
+    host_ascii = None
+    if na > 0:
+        host_ascii = torch.empty(na * a.asm_len, dtype=torch.uint8).pin_memory()
+        host_ascii.copy_(wl.ascii[: na * a.asm_len])
+    a_off = np.ascontiguousarray(wl.contig_off[:nc_a])
+    a_len = np.ascontiguousarray(wl.contig_len[:nc_a])
+    a_acs = np.ascontiguousarray(wl.asm_contig_start[: na + 1])
     del wl.ascii
     wl.ascii = None
     torch.cuda.empty_cache()
@@ -333,10 +370,17 @@ def run_ours(a):
     def e2e_step():
         h, arrays, cig = e2e_h, e2e_arrays, e2e_cig
         nh, ncg = C.c_int64(0), C.c_int64(0)
-        check(L.kb_map_assemblies(gi._h, C.c_void_p(host_ascii.data_ptr()), ptr(e_off), ptr(e_len), ptr(e_acs), ne, C.byref(h),
-                                  C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
+        check(L.kb_map_assemblies_packed(gi._h, C.c_void_p(pin_seq2.data_ptr()), C.c_void_p(pin_mask.data_ptr()), ptr(e_len), ptr(e_acs), ne,
+                                         C.byref(h), C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
         d2h = sum(v.itemsize for v in arrays.values()) * nh.value + 4 * ncg.value
         return nh.value, d2h
+
+    def e2e_ascii_step():
+        h, arrays, cig = e2e_h, e2e_arrays, e2e_cig
+        nh, ncg = C.c_int64(0), C.c_int64(0)
+        check(L.kb_map_assemblies(gi._h, C.c_void_p(host_ascii.data_ptr()), ptr(a_off), ptr(a_len), ptr(a_acs), na, C.byref(h),
+                                  C.byref(nh), ptr(cig), len(cig), C.byref(ncg)))
+        return nh.value
 
     def barrier():
         torch.cuda.synchronize()
@@ -400,7 +444,21 @@ def run_ours(a):
     if dist:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = ne * world / (float(te[0]) / a.steps)
-    h2d = int(host_ascii.numel() + e_off.nbytes + e_len.nbytes + e_acs.nbytes)
+    h2d = int(pin_seq2.numel() * 4 + pin_mask.numel() * 4 + e_len.nbytes + e_acs.nbytes)
+    e2e_ascii = None
+    if na > 0:
+        for _ in range(min(a.warmup, 2)):
+            e2e_ascii_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_ascii_step()
+        barrier()
+        ta = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        e2e_ascii = {"value": na * world / (float(ta[0]) / a.steps), "unit": UNIT, "assemblies_per_step": na,
+                     "h2d_bytes_per_step": int(host_ascii.numel() + a_off.nbytes + a_len.nbytes + a_acs.nbytes)}
 
     if rank != 0:
         if dist:
@@ -457,7 +515,10 @@ def run_ours(a):
         "counters": counters,
         "dp_stats_per_step": dp_stats,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                "assemblies_per_step": ne},
+                "assemblies_per_step": ne, "input": "host-packed 2 bit + N mask in pinned memory (kb_fasta_ingest_pack), kb_map_assemblies_packed",
+                "host_ingest": {"assemblies_per_s": ne / ingest_s, "fasta_gb_per_s": fasta_bytes / ingest_s / 1e9, "threads": ingest_threads,
+                                "note": "FASTA text -> packed pinned buffers on this rank's host threads, outside the timed region"},
+                "ascii": e2e_ascii},
         "gpu_launches": int(counters.get("launches", 0)) * a.steps,
         "clocks": clocks,
         "roofline": roofline,

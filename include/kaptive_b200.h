@@ -83,6 +83,20 @@ int kb_fasta_ingest_parse(const uint8_t *const *data, const int64_t *n, int32_t 
                           int64_t *contig_off, int32_t *contig_len, int32_t *asm_contig_start,
                           int64_t *name_off, int32_t *name_len);
 
+/* Packed ingest: the same FASTA buffers -> 2 bit per base + ambiguity mask, written by the host threads straight into caller
+ * (pinned) buffers in the device layout, so that 0.375 B per base cross PCIe and no pack kernel runs (replaces core/genome.py:45 +
+ * core/seq.py:307-325 for batches; compressed files are opened by the Python layer with the reference's own rules,
+ * core/genome.py:105-106,194-214).  Three passes: kb_fasta_ingest_count (records per file) -> kb_fasta_ingest_lengths (contig
+ * lengths, names) -> kb_packed_layout -> kb_fasta_ingest_pack.
+ * Layout: storage counted in bases; 128 padded bases in front, every contig starts on a multiple of 128 bases, 128 padded bases
+ * behind; seq2 word k = bases 16k..16k+15 (2 bits each, A C G T = 0 1 2 3), nmask word k = bases 32k..32k+31 (1 = ambiguous/padding). */
+int kb_packed_layout(const int32_t *contig_len, int64_t n_contigs, int64_t *contig_soff, int64_t *storage_bases);
+int kb_fasta_ingest_lengths(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads, const int64_t *rec_base,
+                            int32_t *contig_len, int32_t *asm_contig_start, int64_t *name_off, int32_t *name_len);
+int kb_fasta_ingest_pack(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads, const int64_t *rec_base,
+                         const int32_t *contig_len, const int64_t *contig_soff, int64_t storage_bases, uint32_t *seq2, uint32_t *nmask,
+                         int32_t use_simd);
+
 /* ---- gene index: the query side of map_batch (serotyping/core.py:111-121,154) ----
  * Built once per database; device-resident hash of every gene minimizer. */
 typedef struct kb_index kb_index_t;
@@ -103,6 +117,10 @@ int kb_index_deserialize(const uint8_t *buf, int64_t n, int device, kb_index_t *
 typedef struct kb_batch kb_batch_t;
 int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
                     const int32_t *asm_contig_start /* n_asm+1 */, int32_t n_asm, int device, kb_batch_t **out);
+/* The same from host-packed contigs (kb_fasta_ingest_pack): seq2 / nmask are the arrays of a whole ingest call, first_soff the
+ * storage offset (bases) of this batch's first contig in them (kb_packed_layout). */
+int kb_batch_create_packed(const uint32_t *seq2, const uint32_t *nmask, int64_t first_soff, const int32_t *contig_len,
+                           const int32_t *asm_contig_start /* n_asm+1 */, int32_t n_asm, int device, kb_batch_t **out);
 void kb_batch_destroy(kb_batch_t *b);
 int32_t kb_batch_n_assemblies(const kb_batch_t *b);
 int64_t kb_batch_total_bases(const kb_batch_t *b);
@@ -171,6 +189,11 @@ int kb_map_assemblies(const kb_index_t *idx,
                       const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
                       const int32_t *asm_contig_start, int32_t n_asm,
                       kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cigar);
+
+/* the same for host-packed contigs: the end-to-end path of a caller that ingests FASTA with kb_fasta_ingest_pack */
+int kb_map_assemblies_packed(const kb_index_t *idx, const uint32_t *seq2, const uint32_t *nmask, const int32_t *contig_len,
+                             const int32_t *asm_contig_start, int32_t n_asm,
+                             kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cigar);
 
 /* ---- minimizer scan only (the roofline kernel), for benchmarking / parity ----
  * Runs the scan kernel over the batch and returns all minimizers of assembly

@@ -61,6 +61,9 @@ _SYMBOLS = [
     ("kb_fasta_parse", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
     ("kb_fasta_ingest_count", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("kb_fasta_ingest_parse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("kb_packed_layout", C.c_int, [_P, C.c_int64, _P, _P]),
+    ("kb_fasta_ingest_lengths", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    ("kb_fasta_ingest_pack", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, C.c_int32]),
     ("kb_index_create", C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(KbParams), C.c_int, C.POINTER(_P)]),
     ("kb_index_destroy", None, [_P]),
     ("kb_index_n_genes", C.c_int32, [_P]),
@@ -69,6 +72,7 @@ _SYMBOLS = [
     ("kb_index_serialize", C.c_int, [_P, _P, C.c_int64]),
     ("kb_index_deserialize", C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
     ("kb_batch_create", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    ("kb_batch_create_packed", C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     ("kb_batch_destroy", None, [_P]),
     ("kb_batch_n_assemblies", C.c_int32, [_P]),
     ("kb_batch_total_bases", C.c_int64, [_P]),
@@ -86,6 +90,7 @@ _SYMBOLS = [
     ("kb_debug_dp_stats", C.c_int, [_P, C.c_int]),
     ("kb_debug_dp", C.c_int, [C.POINTER(KbParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32]),
     ("kb_map_assemblies", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(KbHits), _P, _P, C.c_int64, _P]),
+    ("kb_map_assemblies_packed", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(KbHits), _P, _P, C.c_int64, _P]),
     ("kb_scan_minimizers", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     ("kb_bench_scan", C.c_int, [_P, _P, C.c_int, _P, _P]),
     ("kb_post_last_error", C.c_char_p, []),

@@ -16,6 +16,8 @@
 #include "kb_host.h"
 #include "kb_kernels.h"
 
+extern "C" int kb_packed_layout(const int32_t *contig_len, int64_t n_contigs, int64_t *contig_soff, int64_t *storage_bases);
+
 // ---- prototypes of the launchers in kb_pipeline.cu
 void kb_launch_pack(const uint8_t *, int64_t, const int64_t *, const int64_t *, const int32_t *, int32_t, int32_t, int64_t, int64_t,
                     uint32_t *, uint32_t *, cudaStream_t);
@@ -312,8 +314,12 @@ int kb_index_deserialize(const uint8_t *buf, int64_t n, int device, kb_index_t *
     return KB_OK;
 }
 
-int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len, const int32_t *asm_contig_start,
-                    int32_t n_asm, int device, kb_batch_t **out)
+}  // extern "C"
+
+// Common part of the two batch constructors: layout, device arrays, view.  `fill(b, st, d_off)` puts the sequence in place.
+template <class Fill>
+static int batch_create_common(const int64_t *contig_off, const int32_t *contig_len, const int32_t *asm_contig_start, int32_t n_asm, int device,
+                               kb_batch_t **out, Fill fill)
 {
     if (!out || !asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
     int ndev = 0;
@@ -326,7 +332,6 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         return fail(KB_ERR_LIMIT, err);
     }
     cudaStream_t st = nullptr;
-    uint8_t *d_ascii = nullptr;
     try {
         CU(cudaSetDevice(device));
         setup_mempool(device);
@@ -335,7 +340,8 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         b->n_sm = prop.multiProcessorCount;
         b->device = device;
         const KbHostBatchLayout &L = b->L;
-        std::vector<int64_t> off_v(contig_off, contig_off + L.n_ctg);
+        std::vector<int64_t> off_v;
+        if (contig_off) off_v.assign(contig_off, contig_off + L.n_ctg);
         std::vector<uint8_t> blob;
         size_t o_so = put_blob(blob, L.ctg_soff), o_len = put_blob(blob, L.ctg_len), o_asm = put_blob(blob, L.ctg_asm);
         size_t o_vs = put_blob(blob, L.ctg_vstart), o_acs = put_blob(blob, L.asm_ctg_start), o_cc = put_blob(blob, L.chunk_ctg);
@@ -347,9 +353,6 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         CU(cudaMemcpyAsync(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
         CU(cudaMallocAsync((void **)&b->seq2, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
         CU(cudaMallocAsync((void **)&b->nmask, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
-        // lead-in / tail padding groups
-        CU(cudaMemsetAsync(b->seq2, 0, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
-        CU(cudaMemsetAsync(b->nmask, 0xff, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
         uint8_t *db = b->d_blob;
         KbBatchView &v = b->view;
         v.n_asm = L.n_asm, v.n_ctg = L.n_ctg, v.n_chunks = (int64_t)L.chunk_ctg.size(), v.total_bases = L.total_bases;
@@ -357,40 +360,11 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
         v.ctg_soff = (const int64_t *)(db + o_so), v.ctg_len = (const int32_t *)(db + o_len), v.ctg_asm = (const int32_t *)(db + o_asm);
         v.ctg_vstart = (const int32_t *)(db + o_vs), v.asm_ctg_start = (const int32_t *)(db + o_acs);
         v.chunk_ctg = (const int32_t *)(db + o_cc), v.chunk_start = (const int32_t *)(db + o_cs);
-        const int64_t *d_off = (const int64_t *)(db + o_off);
-        // pack in slabs of <= 1 GiB of ASCII so the transient staging buffer stays bounded
-        const int64_t slab = (int64_t)1 << 30;
-        int c0 = 0;
-        int64_t staged_cap = 0;
-        while (c0 < L.n_ctg) {
-            int64_t lo = contig_off[c0], hi = lo;
-            int c1 = c0;
-            while (c1 < L.n_ctg) {
-                int64_t a = contig_off[c1], e = a + L.ctg_len[c1];
-                int64_t nlo = a < lo ? a : lo, nhi = e > hi ? e : hi;
-                if (c1 > c0 && nhi - nlo > slab) break;
-                lo = nlo, hi = nhi, ++c1;
-            }
-            int64_t bytes = hi - lo;
-            if (bytes > staged_cap) {
-                if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
-                staged_cap = bytes + 64;
-                CU(cudaMallocAsync((void **)&d_ascii, (size_t)staged_cap, st));
-            }
-            if (bytes > 0) CU(cudaMemcpyAsync(d_ascii, contig_seqs + lo, (size_t)bytes, cudaMemcpyDefault, st));
-            int64_t g0 = L.ctg_soff[c0] >> 5;
-            int64_t g1 = (c1 < L.n_ctg ? L.ctg_soff[c1] : L.storage_bases - 128) >> 5;
-            kb_launch_pack(d_ascii, lo, d_off, v.ctg_soff, v.ctg_len, c0, c1, g0, g1, b->seq2, b->nmask, st);
-            CU(cudaGetLastError());
-            c0 = c1;
-        }
-        if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
-        d_ascii = nullptr;
+        fill(b, st, (const int64_t *)(db + o_off));
         CU(cudaStreamSynchronize(st));
         CU(cudaStreamDestroy(st));
     } catch (const std::string &e) {
         if (st) cudaStreamSynchronize(st), cudaStreamDestroy(st);
-        if (d_ascii) cudaFreeAsync(d_ascii, 0);
         if (b->d_blob) cudaFreeAsync(b->d_blob, 0);
         if (b->seq2) cudaFreeAsync(b->seq2, 0);
         if (b->nmask) cudaFreeAsync(b->nmask, 0);
@@ -399,6 +373,81 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
     }
     *out = b;
     return KB_OK;
+}
+
+extern "C" {
+
+int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len, const int32_t *asm_contig_start,
+                    int32_t n_asm, int device, kb_batch_t **out)
+{
+    if (n_asm > 0 && asm_contig_start && asm_contig_start[n_asm] > 0 && (!contig_seqs || !contig_off || !contig_len)) return fail(KB_ERR_ARG, "null argument");
+    return batch_create_common(contig_off, contig_len, asm_contig_start, n_asm, device, out, [&](kb_batch *b, cudaStream_t st, const int64_t *d_off) {
+        const KbHostBatchLayout &L = b->L;
+        const KbBatchView &v = b->view;
+        // lead-in / tail padding groups
+        CU(cudaMemsetAsync(b->seq2, 0, (size_t)(L.storage_bases >> 4) * 4 + 64, st));
+        CU(cudaMemsetAsync(b->nmask, 0xff, (size_t)(L.storage_bases >> 5) * 4 + 64, st));
+        // pack in slabs of <= 1 GiB of ASCII so the transient staging buffer stays bounded
+        const int64_t slab = (int64_t)1 << 30;
+        uint8_t *d_ascii = nullptr;
+        int c0 = 0;
+        int64_t staged_cap = 0;
+        try {
+            while (c0 < L.n_ctg) {
+                int64_t lo = contig_off[c0], hi = lo;
+                int c1 = c0;
+                while (c1 < L.n_ctg) {
+                    int64_t a = contig_off[c1], e = a + L.ctg_len[c1];
+                    int64_t nlo = a < lo ? a : lo, nhi = e > hi ? e : hi;
+                    if (c1 > c0 && nhi - nlo > slab) break;
+                    lo = nlo, hi = nhi, ++c1;
+                }
+                int64_t bytes = hi - lo;
+                if (bytes > staged_cap) {
+                    if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
+                    d_ascii = nullptr;
+                    staged_cap = bytes + 64;
+                    CU(cudaMallocAsync((void **)&d_ascii, (size_t)staged_cap, st));
+                }
+                if (bytes > 0) CU(cudaMemcpyAsync(d_ascii, contig_seqs + lo, (size_t)bytes, cudaMemcpyDefault, st));
+                int64_t g0 = L.ctg_soff[c0] >> 5;
+                int64_t g1 = (c1 < L.n_ctg ? L.ctg_soff[c1] : L.storage_bases - 128) >> 5;
+                kb_launch_pack(d_ascii, lo, d_off, v.ctg_soff, v.ctg_len, c0, c1, g0, g1, b->seq2, b->nmask, st);
+                CU(cudaGetLastError());
+                c0 = c1;
+            }
+        } catch (...) {
+            if (d_ascii) cudaFreeAsync(d_ascii, st);
+            throw;
+        }
+        if (d_ascii) CU(cudaFreeAsync(d_ascii, st));
+    });
+}
+
+// Contigs that are already 2-bit packed on the host (kb_fasta_ingest_pack): seq2 / nmask are the arrays of a whole ingest call in
+// the layout of kb_packed_layout, `first_soff` the storage offset (in bases) of this batch's first contig in them.  The batch's own
+// layout is the same rule started afresh, so its storage is the host range [first_soff, first_soff + storage - 256) moved to 128.
+int kb_batch_create_packed(const uint32_t *seq2, const uint32_t *nmask, int64_t first_soff, const int32_t *contig_len,
+                           const int32_t *asm_contig_start, int32_t n_asm, int device, kb_batch_t **out)
+{
+    if (!seq2 || !nmask || first_soff < 128 || (first_soff & 127)) return fail(KB_ERR_ARG, "bad packed buffers / first_soff");
+    return batch_create_common(nullptr, contig_len, asm_contig_start, n_asm, device, out, [&](kb_batch *b, cudaStream_t st, const int64_t *) {
+        const KbHostBatchLayout &L = b->L;
+        const size_t ws = (size_t)(L.storage_bases >> 4), wm = (size_t)(L.storage_bases >> 5);
+        // lead-in and tail groups (128 bases = 8 sequence words, 4 mask words each) are padding; the rest comes from the host
+        CU(cudaMemsetAsync(b->seq2, 0, 8 * 4, st));
+        CU(cudaMemsetAsync(b->nmask, 0xff, 4 * 4, st));
+        CU(cudaMemsetAsync(b->seq2 + ws - 8, 0, 8 * 4 + 64, st));
+        CU(cudaMemsetAsync(b->nmask + wm - 4, 0xff, 4 * 4 + 64, st));
+        const int64_t body = L.storage_bases - 256;  // bases
+        // in pieces of 64 MiB so that a scan launched behind it on another stream is never starved of copy-engine slots for long
+        const int64_t piece = (int64_t)1 << 28;  // bases
+        for (int64_t o = 0; o < body; o += piece) {
+            const int64_t nb = body - o < piece ? body - o : piece;
+            CU(cudaMemcpyAsync(b->seq2 + 8 + (o >> 4), seq2 + ((first_soff + o) >> 4), (size_t)(nb >> 4) * 4, cudaMemcpyDefault, st));
+            CU(cudaMemcpyAsync(b->nmask + 4 + (o >> 5), nmask + ((first_soff + o) >> 5), (size_t)(nb >> 5) * 4, cudaMemcpyDefault, st));
+        }
+    });
 }
 
 void kb_batch_destroy(kb_batch_t *b)
@@ -892,32 +941,21 @@ int kb_result_fetch_chains(const kb_result_t *r, int32_t *out, int64_t cap, int6
     return KB_OK;
 }
 
+}  // extern "C"
+
 static std::mutex g_h2d_mu;  // one slab copies at a time: two concurrent H2D streams only halve each other's bandwidth
-static int map_assemblies_once(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
-                               const int32_t *asm_contig_start, int32_t n_asm, kb_result_t **out)
-{
-    kb_batch_t *b = nullptr;
-    int rc;
-    {
-        std::lock_guard<std::mutex> lk(g_h2d_mu);
-        rc = kb_batch_create(contig_seqs, contig_off, contig_len, asm_contig_start, n_asm, ix->device, &b);
-    }
-    if (rc) return rc;
-    rc = kb_map_batch(ix, b, out);
-    kb_batch_destroy(b);
-    return rc;
-}
 
 // Host buffers in, host arrays out.  Calls of 512 assemblies or more are cut into equal slabs (at least two, at most
 // KAPTIVE_B200_SLAB = 768 assemblies each) that two host threads push through batch_create -> map on their own streams, which
-// bounds the device memory of a call and lets the H2D copy and packing of one slab overlap the kernels of the other; the
+// bounds the device memory of a call and lets the H2D copy (and packing) of one slab overlap the kernels of the other; the
 // slabs' hits are then fetched in assembly order.  Slabs must stay large: measured on B200 (scripts/e2e_probe.py, 1000
 // assemblies per call) one slab takes 418 ms, two 382 ms, four 390 ms, six on three threads 440 ms and more -- small slabs
 // lose more to half-empty persistent kernels than the overlap wins.  Results do not depend on the slab size (assemblies
 // are independent units; tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
-int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
-                      const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
-                      int64_t cigar_cap, int64_t *n_cigar)
+// make_batch(a0, a1, c0, acs) builds the device batch of assemblies [a0, a1) (contigs from c0, acs = their contig ranges from 0).
+template <class MakeBatch>
+static int map_slabs(const kb_index_t *ix, const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
+                     int64_t cigar_cap, int64_t *n_cigar, MakeBatch make_batch)
 {
     if (!ix) return fail(KB_ERR_ARG, "null index");
     if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
@@ -952,8 +990,18 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
         const int c0 = asm_contig_start[a0];
         std::vector<int32_t> acs((size_t)(a1 - a0) + 1);
         for (int a = a0; a <= a1; ++a) acs[(size_t)(a - a0)] = asm_contig_start[a] - c0;
-        rcs[(size_t)k] = map_assemblies_once(ix, contig_seqs, contig_off + c0, contig_len + c0, acs.data(), a1 - a0, &res[(size_t)k]);
-        if (rcs[(size_t)k]) errs[(size_t)k] = g_err;  // g_err is thread local
+        kb_batch_t *b = nullptr;
+        int rc;
+        {
+            std::lock_guard<std::mutex> lk(g_h2d_mu);
+            rc = make_batch(a0, a1, c0, acs.data(), &b);
+        }
+        if (!rc) {
+            rc = kb_map_batch(ix, b, &res[(size_t)k]);
+            kb_batch_destroy(b);
+        }
+        rcs[(size_t)k] = rc;
+        if (rc) errs[(size_t)k] = g_err;  // g_err is thread local
     };
     if (n_slabs == 1) run_slab(0);
     else {
@@ -1004,6 +1052,35 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
     }
     for (kb_result_t *r : res) kb_result_destroy(r);
     return rc;
+}
+
+extern "C" {
+
+int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const int64_t *contig_off, const int32_t *contig_len,
+                      const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
+                      int64_t cigar_cap, int64_t *n_cigar)
+{
+    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar,
+                     [&](int a0, int a1, int c0, const int32_t *acs, kb_batch_t **b) {
+                         return kb_batch_create(contig_seqs, contig_off + c0, contig_len + c0, acs, a1 - a0, ix->device, b);
+                     });
+}
+
+// The same for contigs the host has already packed (kb_fasta_ingest_pack): 0.375 B per base cross PCIe, no pack kernel.
+int kb_map_assemblies_packed(const kb_index_t *ix, const uint32_t *seq2, const uint32_t *nmask, const int32_t *contig_len,
+                             const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
+                             int64_t cigar_cap, int64_t *n_cigar)
+{
+    if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
+    const int64_t n_ctg = n_asm ? asm_contig_start[n_asm] : 0;
+    std::vector<int64_t> soff((size_t)n_ctg + 1);
+    int64_t storage = 0;
+    if (kb_packed_layout(contig_len, n_ctg, soff.data(), &storage) != KB_OK) return fail(KB_ERR_ARG, "bad contig lengths");
+    soff[(size_t)n_ctg] = storage - 128;
+    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar,
+                     [&](int a0, int a1, int c0, const int32_t *acs, kb_batch_t **b) {
+                         return kb_batch_create_packed(seq2, nmask, soff[(size_t)c0], contig_len + c0, acs, a1 - a0, ix->device, b);
+                     });
 }
 
 int kb_release_workspace(int device)

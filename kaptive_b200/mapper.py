@@ -97,6 +97,17 @@ class AssemblyBatch:
         batch.contig_names = b.names
         return batch
 
+    @classmethod
+    def from_packed(cls, pb, device: int = 0) -> "AssemblyBatch":
+        """Host-packed contigs (``ingest.ingest_fasta_packed``) -> device batch: the 2-bit words go over PCIe as they are."""
+        L = _lib.load()
+        self = cls.__new__(cls)
+        self.device, self.n_asm, self._h = device, len(pb.asm_contig_start) - 1, C.c_void_p(0)
+        check(L.kb_batch_create_packed(ptr(pb.seq2), ptr(pb.nmask), 128, ptr(pb.contig_len), ptr(pb.asm_contig_start), self.n_asm, device,
+                                       C.byref(self._h)))
+        self.contig_lengths, self.asm_contig_start, self.contig_names = pb.contig_len, pb.asm_contig_start, pb.names
+        return self
+
     @property
     def total_bases(self) -> int:
         return int(_lib.load().kb_batch_total_bases(self._h))
@@ -167,6 +178,21 @@ class GeneIndex:
             return self.map(b)
         finally:
             b.close()
+
+    def map_packed(self, pb, out=None) -> MapResult:
+        """Host-packed assemblies in, hits out, through the one-call C-ABI entry ``kb_map_assemblies_packed`` (slabs, copies inside)."""
+        L = _lib.load()
+        n_asm = len(pb.asm_contig_start) - 1
+        if out is None:
+            h, arrays = alloc_hits(1024 * max(n_asm, 1))
+            cig = np.zeros(1024 * max(n_asm, 1) * 16, dtype=np.uint32)
+        else:
+            h, arrays, cig = out
+        nh, nc = C.c_int64(0), C.c_int64(0)
+        check(L.kb_map_assemblies_packed(self._h, ptr(pb.seq2), ptr(pb.nmask), ptr(pb.contig_len), ptr(pb.asm_contig_start), n_asm, C.byref(h),
+                                         C.byref(nh), ptr(cig), len(cig), C.byref(nc)))
+        return MapResult(hits={k: v[: nh.value] for k, v in arrays.items()}, cigar=cig[: nc.value], stage_ms={}, counters={},
+                         mid_occ=np.zeros(0, np.int32))
 
     def bench_scan(self, batch: AssemblyBatch, iters: int = 5) -> tuple[float, int]:
         ms = C.c_float(0)

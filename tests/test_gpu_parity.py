@@ -340,6 +340,33 @@ def test_batch_fasta_ingest_feeds_the_mapper(env):
         check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
 
 
+def test_packed_ingest_from_fasta_gz_feeds_the_mapper(env, tmp_path, monkeypatch):
+    """FASTA(.gz) files -> ingest.read_fasta_files (the reference's openers) -> kb_fasta_ingest_pack (2 bit + N mask on the host)
+    -> kb_batch_create_packed / kb_map_assemblies_packed (slabs of 2 assemblies) -> the golden hits: the host packer and the device
+    pack kernel are interchangeable."""
+    import gzip
+
+    from kaptive_b200 import ingest
+
+    names = ["fragmented", "lowercase", "n_rich", "empty_assembly", "two_loci", "tiny_contigs", "boundaries"]
+    paths = []
+    for k, n in enumerate(names):
+        data = cases.fasta_bytes(env["built"][n][1])
+        p = tmp_path / (f"{n}.fasta.gz" if k % 2 == 0 else f"{n}.fna")
+        p.write_bytes(gzip.compress(data) if k % 2 == 0 else data)
+        paths.append(p)
+    blobs, ids = ingest.read_fasta_files(paths, threads=4)
+    assert ids == names
+    pb = ingest.ingest_fasta_packed(blobs, threads=4)
+    res = env["gi"].map(env["mapper"].AssemblyBatch.from_packed(pb), fetch=True)
+    for ai, n in enumerate(names):
+        check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
+    monkeypatch.setenv("KAPTIVE_B200_SLAB", "2")
+    res2 = env["gi"].map_packed(pb)
+    for ai, n in enumerate(names):
+        check_against(res2, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
+
+
 def test_one_warp_per_chain_kernel_alone_gives_the_same_hits(env, monkeypatch):
     """KAPTIVE_B200_STAGED=0 sends every chain through kb_align_kernel (all of mm_align1 in one warp), the kernel that
     otherwise only serves the chains the staged path hands back: it has to stay bit-identical."""

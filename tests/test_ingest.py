@@ -86,3 +86,94 @@ def test_preallocated_output_buffer_and_empty_batch():
         ingest.ingest_fasta(files, out=np.zeros(3, np.uint8))
     e = ingest.ingest_fasta([])
     assert len(e.seqs) == 0 and list(e.asm_contig_start) == [0]
+
+
+# ---------------------------------------------------------------------------------------------- packed ingest
+_CODE = np.full(256, 4, np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _CODE[_c | 0x20] = _i
+_CODE[ord("U")] = _CODE[ord("u")] = 3
+
+
+def unpack(pb, c):
+    """Contig c of a PackedBatch back to nt4 codes (4 = ambiguous)."""
+    so, ln = int(pb.contig_soff[c]), int(pb.contig_len[c])
+    b = so + np.arange(ln, dtype=np.int64)
+    code = (pb.seq2[b >> 4] >> (2 * (b & 15)).astype(np.uint32)) & 3
+    amb = (pb.nmask[b >> 5] >> (b & 31).astype(np.uint32)) & 1
+    return np.where(amb == 1, 4, code).astype(np.uint8)
+
+
+def make_files_with_ambiguity():
+    rng = np.random.default_rng(5)
+    files = make_files()
+    parts = []
+    for c in range(6):
+        s = np.frombuffer(synth.random_dna(rng, int(rng.integers(1, 3000))).tobytes(), np.uint8).copy()
+        s[rng.integers(0, len(s), size=max(1, len(s) // 50))] = np.frombuffer(b"NnRYKMSWUu-*", np.uint8)[rng.integers(0, 12, size=max(1, len(s) // 50))]
+        w = int(rng.choice([60, 61, 80, 127, 128, 129]))
+        parts.append(b">amb%d\n" % c)
+        parts.extend(s[k : k + w].tobytes() + b"\n" for k in range(0, len(s), w))
+    files.insert(3, b"".join(parts))
+    return files
+
+
+@pytest.mark.parametrize("threads,simd", [(1, True), (7, True), (3, False)])
+def test_packed_ingest_equals_the_ascii_path(threads, simd):
+    """kb_fasta_ingest_count / _lengths / kb_packed_layout / kb_fasta_ingest_pack: every contig, unpacked, equals the nt4 codes of
+    the bytes the ASCII reader yields; padding is ambiguous, sequence words of padding are zero; the AVX2 + BMI2 packer and the
+    portable loop are bit-identical; the layout is the device's (contigs on 128-base boundaries, 128 padded bases at both ends)."""
+    files = make_files_with_ambiguity()
+    ref = ingest.ingest_fasta(files, threads=2)
+    pb = ingest.ingest_fasta_packed(files, threads=threads, use_simd=simd)
+    assert np.array_equal(pb.asm_contig_start, ref.asm_contig_start) and np.array_equal(pb.contig_len, ref.contig_len)
+    assert pb.names == ref.names
+    assert pb.storage_bases % 128 == 0 and len(pb.seq2) == pb.storage_bases // 16 and len(pb.nmask) == pb.storage_bases // 32
+    covered = np.zeros(pb.storage_bases, bool)
+    for c in range(len(pb.contig_len)):
+        so, ln = int(pb.contig_soff[c]), int(pb.contig_len[c])
+        assert so % 128 == 0 and so >= 128
+        o = int(ref.contig_off[c])
+        assert np.array_equal(unpack(pb, c), _CODE[ref.seqs[o : o + ln]]), c
+        covered[so : so + ln] = True
+    # everything that is not a base of some contig: mask bit set, sequence bits zero
+    b = np.nonzero(~covered)[0]
+    assert np.all((pb.nmask[b >> 5] >> (b & 31).astype(np.uint32)) & 1 == 1)
+    assert np.all((pb.seq2[b >> 4] >> (2 * (b & 15)).astype(np.uint32)) & 3 == 0)
+    other = ingest.ingest_fasta_packed(files, threads=2, use_simd=not simd)
+    assert np.array_equal(other.seq2, pb.seq2) and np.array_equal(other.nmask, pb.nmask)
+
+
+def test_packed_ingest_into_caller_buffers_and_empty_input():
+    files = make_files()
+    pb0 = ingest.ingest_fasta_packed(files, threads=2)
+    seq2, nmask = np.full(len(pb0.seq2) + 100, 0xDEADBEEF, np.uint32), np.full(len(pb0.nmask) + 100, 0x12345678, np.uint32)
+    pb = ingest.ingest_fasta_packed(files, threads=3, out=(seq2, nmask))
+    assert np.array_equal(pb.seq2, pb0.seq2) and np.array_equal(pb.nmask, pb0.nmask)
+    assert seq2[len(pb0.seq2)] == 0xDEADBEEF and nmask[len(pb0.nmask)] == 0x12345678  # nothing written past the layout
+    e = ingest.ingest_fasta_packed([], threads=1)
+    assert e.storage_bases == 256 and np.all(e.nmask == 0xFFFFFFFF) and np.all(e.seq2 == 0)
+    e = ingest.ingest_fasta_packed([b"", b">x\n", b""], threads=2)
+    assert e.asm_contig_start.tolist() == [0, 0, 1, 1] and e.contig_len.tolist() == [0] and np.all(e.nmask == 0xFFFFFFFF)
+
+
+def test_read_fasta_files_follows_the_reference_openers(tmp_path):
+    """File-name rules and compression formats of GenomeAssembly.from_file (reference core/genome.py:105-106,194-214)."""
+    import bz2
+    import gzip
+    import lzma
+
+    data = b">c1 d\nACGTNNAC\nGT\n>c2\nTTTT\n"
+    (tmp_path / "a.fasta").write_bytes(data)
+    (tmp_path / "b.fna.gz").write_bytes(gzip.compress(data))
+    (tmp_path / "c.fa.bz2").write_bytes(bz2.compress(data))
+    (tmp_path / "d.fas.xz").write_bytes(lzma.compress(data))
+    paths = [tmp_path / n for n in ("a.fasta", "b.fna.gz", "c.fa.bz2", "d.fas.xz")]
+    blobs, ids = ingest.read_fasta_files(paths, threads=3)
+    assert blobs == [data] * 4 and ids == ["a", "b", "c", "d"]
+    pb = ingest.ingest_fasta_packed(blobs, threads=2)
+    assert pb.contig_len.tolist() == [10, 4] * 4 and pb.names[1] == ["c1", "c2"]
+    assert unpack(pb, 0).tolist() == [0, 1, 2, 3, 4, 4, 0, 1, 2, 3]
+    (tmp_path / "e.txt").write_bytes(data)
+    with pytest.raises(NotImplementedError):
+        ingest.read_fasta_files([tmp_path / "e.txt"])
