@@ -86,10 +86,11 @@ int kb_fasta_ingest_parse(const uint8_t *const *data, const int64_t *n, int32_t 
 /* Packed ingest: the same FASTA buffers -> 2 bit per base + ambiguity mask, written by the host threads straight into caller
  * (pinned) buffers in the device layout, so that 0.375 B per base cross PCIe and no pack kernel runs (replaces core/genome.py:45 +
  * core/seq.py:307-325 for batches; compressed files are opened by the Python layer with the reference's own rules,
- * core/genome.py:105-106,194-214).  Three passes: kb_fasta_ingest_count (records per file) -> kb_fasta_ingest_lengths (contig
+ * core/genome.py:105-106,194-214).  Three passes: kb_fasta_ingest_count_records (records per file) -> kb_fasta_ingest_lengths (contig
  * lengths, names) -> kb_packed_layout -> kb_fasta_ingest_pack.
  * Layout: storage counted in bases; 128 padded bases in front, every contig starts on a multiple of 128 bases, 128 padded bases
  * behind; seq2 word k = bases 16k..16k+15 (2 bits each, A C G T = 0 1 2 3), nmask word k = bases 32k..32k+31 (1 = ambiguous/padding). */
+int kb_fasta_ingest_count_records(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads, int64_t *n_records);
 int kb_packed_layout(const int32_t *contig_len, int64_t n_contigs, int64_t *contig_soff, int64_t *storage_bases);
 int kb_fasta_ingest_lengths(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads, const int64_t *rec_base,
                             int32_t *contig_len, int32_t *asm_contig_start, int64_t *name_off, int32_t *name_len);
@@ -121,6 +122,8 @@ int kb_batch_create(const uint8_t *contig_seqs, const int64_t *contig_off, const
  * storage offset (bases) of this batch's first contig in them (kb_packed_layout). */
 int kb_batch_create_packed(const uint32_t *seq2, const uint32_t *nmask, int64_t first_soff, const int32_t *contig_len,
                            const int32_t *asm_contig_start /* n_asm+1 */, int32_t n_asm, int device, kb_batch_t **out);
+/* the batch's packed words copied back to the host (storage_bases / 16 and / 32 words; either pointer may be null) */
+int kb_batch_download_packed(const kb_batch_t *b, uint32_t *seq2, uint32_t *nmask, int64_t *storage_bases);
 void kb_batch_destroy(kb_batch_t *b);
 int32_t kb_batch_n_assemblies(const kb_batch_t *b);
 int64_t kb_batch_total_bases(const kb_batch_t *b);

@@ -61,6 +61,7 @@ _SYMBOLS = [
     ("kb_fasta_parse", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64, _P, _P]),
     ("kb_fasta_ingest_count", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("kb_fasta_ingest_parse", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("kb_fasta_ingest_count_records", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     ("kb_packed_layout", C.c_int, [_P, C.c_int64, _P, _P]),
     ("kb_fasta_ingest_lengths", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     ("kb_fasta_ingest_pack", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, C.c_int32]),
@@ -73,6 +74,7 @@ _SYMBOLS = [
     ("kb_index_deserialize", C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
     ("kb_batch_create", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     ("kb_batch_create_packed", C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    ("kb_batch_download_packed", C.c_int, [_P, _P, _P, _P]),
     ("kb_batch_destroy", None, [_P]),
     ("kb_batch_n_assemblies", C.c_int32, [_P]),
     ("kb_batch_total_bases", C.c_int64, [_P]),

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <cstring>
@@ -448,6 +449,21 @@ int kb_batch_create_packed(const uint32_t *seq2, const uint32_t *nmask, int64_t 
             CU(cudaMemcpyAsync(b->nmask + 4 + (o >> 5), nmask + ((first_soff + o) >> 5), (size_t)(nb >> 5) * 4, cudaMemcpyDefault, st));
         }
     });
+}
+
+// the batch's packed words back on the host (layout of kb_packed_layout over the batch's own contigs): storage / 16 and
+// storage / 32 words.  Parity tests compare the device pack kernel with the host packer through it; bench.py builds its pinned
+// end-to-end input from the resident batch with it.
+int kb_batch_download_packed(const kb_batch_t *b, uint32_t *seq2, uint32_t *nmask, int64_t *storage_bases)
+{
+    if (!b) return fail(KB_ERR_ARG, "null batch");
+    if (storage_bases) *storage_bases = b->L.storage_bases;
+    if (!seq2 && !nmask) return KB_OK;
+    if (cudaSetDevice(b->device) != cudaSuccess) return fail(KB_ERR_CUDA, "cudaSetDevice failed");
+    if (seq2 && cudaMemcpy(seq2, b->seq2, (size_t)(b->L.storage_bases >> 4) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(KB_ERR_CUDA, "D2H of seq2 failed");
+    if (nmask && cudaMemcpy(nmask, b->nmask, (size_t)(b->L.storage_bases >> 5) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(KB_ERR_CUDA, "D2H of nmask failed");
+    return KB_OK;
 }
 
 void kb_batch_destroy(kb_batch_t *b)
@@ -943,19 +959,16 @@ int kb_result_fetch_chains(const kb_result_t *r, int32_t *out, int64_t cap, int6
 
 }  // extern "C"
 
-static std::mutex g_h2d_mu;  // one slab copies at a time: two concurrent H2D streams only halve each other's bandwidth
-
-// Host buffers in, host arrays out.  Calls of 512 assemblies or more are cut into equal slabs (at least two, at most
-// KAPTIVE_B200_SLAB = 768 assemblies each) that two host threads push through batch_create -> map on their own streams, which
-// bounds the device memory of a call and lets the H2D copy (and packing) of one slab overlap the kernels of the other; the
-// slabs' hits are then fetched in assembly order.  Slabs must stay large: measured on B200 (scripts/e2e_probe.py, 1000
-// assemblies per call) one slab takes 418 ms, two 382 ms, four 390 ms, six on three threads 440 ms and more -- small slabs
-// lose more to half-empty persistent kernels than the overlap wins.  Results do not depend on the slab size (assemblies
-// are independent units; tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
+// Host buffers in, host arrays out.  Calls of 512 assemblies or more are cut into slabs (ASCII input: equal slabs of at most
+// KAPTIVE_B200_SLAB = 768 assemblies; packed input: a short first slab, then large ones), which bounds the device memory of a
+// call and lets the H2D copy (and packing) of one slab run under the kernels of the previous one; hits come back in assembly
+// order.  Slabs must stay large: small slabs lose more to half-empty persistent kernels than the overlap wins (measured,
+// scripts/e2e_probe.py).  Results do not depend on the slab plan (assemblies are independent units;
+// tests/test_gpu_parity.py::test_host_buffer_entry_point_slabs_equal_batch_path).
 // make_batch(a0, a1, c0, acs) builds the device batch of assemblies [a0, a1) (contigs from c0, acs = their contig ranges from 0).
 template <class MakeBatch>
 static int map_slabs(const kb_index_t *ix, const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
-                     int64_t cigar_cap, int64_t *n_cigar, MakeBatch make_batch)
+                     int64_t cigar_cap, int64_t *n_cigar, bool packed, MakeBatch make_batch)
 {
     if (!ix) return fail(KB_ERR_ARG, "null index");
     if (!asm_contig_start || n_asm < 0) return fail(KB_ERR_ARG, "null argument");
@@ -971,6 +984,16 @@ static int map_slabs(const kb_index_t *ix, const int32_t *asm_contig_start, int3
             const char *c = strchr(q, ',');
             q = c ? c + 1 : "";
         }
+    } else if (packed && !getenv("KAPTIVE_B200_SLAB") && n_asm >= 1024) {
+        // packed input: the copy of a slab (0.375 B per base) is several times shorter than its kernels, so only the FIRST slab's copy
+        // is ever exposed: a short first slab, then slabs as large as possible (the persistent DP kernels lose ~10 % at 700
+        // assemblies per launch against 2500; device memory is not a constraint at 1.9 MB per assembly)
+        // sizes 512, 1536, then equal slabs of at most 2560: the copy of slab k + 1 (0.075 ms per assembly at 25 GB/s) always ends
+        // before the kernels of slab k (0.27 ms per assembly) do
+        bnd.push_back(std::min(512, n_asm / 4));
+        if (n_asm - bnd.back() > 2 * 1536) bnd.push_back(bnd.back() + 1536);
+        const int base = bnd.back(), rest = n_asm - base, n = (rest + 2559) / 2560, each = (rest + n - 1) / n;
+        for (int k = 1; k <= n; ++k) bnd.push_back(std::min(n_asm, base + k * each));
     } else {
         int slab = 768, n;
         if (const char *e = getenv("KAPTIVE_B200_SLAB")) {  // explicit slab size: cut whenever the call is larger
@@ -982,57 +1005,61 @@ static int map_slabs(const kb_index_t *ix, const int32_t *asm_contig_start, int3
     }
     if (bnd.back() < n_asm || bnd.size() < 2) bnd.assign({0, n_asm});
     const int n_slabs = (int)bnd.size() - 1;
-    std::vector<kb_result_t *> res((size_t)n_slabs, nullptr);
-    std::vector<int> rcs((size_t)n_slabs, KB_OK);
-    std::vector<std::string> errs((size_t)n_slabs);
-    auto run_slab = [&](int k) {
-        const int a0 = bnd[(size_t)k], a1 = bnd[(size_t)k + 1];
-        const int c0 = asm_contig_start[a0];
-        std::vector<int32_t> acs((size_t)(a1 - a0) + 1);
-        for (int a = a0; a <= a1; ++a) acs[(size_t)(a - a0)] = asm_contig_start[a] - c0;
-        kb_batch_t *b = nullptr;
-        int rc;
-        {
-            std::lock_guard<std::mutex> lk(g_h2d_mu);
-            rc = make_batch(a0, a1, c0, acs.data(), &b);
+    // A producer thread builds the device batches in order (host -> device copy, and the pack kernel for ASCII input), at most two
+    // ahead of the consumer; this thread maps them one after the other and fetches each slab's hits as soon as they exist.  One
+    // mapping call at a time keeps the persistent kernels of two slabs from competing for the SMs, while the copy engine works
+    // under them (measured against two threads that each did copy + map: 3270 -> 3480 assemblies/s end to end at 10,000 per call).
+    std::vector<kb_batch_t *> ready((size_t)n_slabs, nullptr);
+    std::vector<int> made((size_t)n_slabs, 0), mk_rc((size_t)n_slabs, KB_OK);
+    std::vector<std::string> mk_err((size_t)n_slabs);
+    std::mutex mu;
+    std::condition_variable cv;
+    int consumed = 0;
+    bool stop = false;
+    std::thread producer([&]() {
+        for (int k = 0; k < n_slabs; ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || k < consumed + 2; });
+                if (stop) return;
+            }
+            const int a0 = bnd[(size_t)k], a1 = bnd[(size_t)k + 1];
+            const int c0 = asm_contig_start[a0];
+            std::vector<int32_t> acs((size_t)(a1 - a0) + 1);
+            for (int a = a0; a <= a1; ++a) acs[(size_t)(a - a0)] = asm_contig_start[a] - c0;
+            kb_batch_t *b = nullptr;
+            const int rc = make_batch(a0, a1, c0, acs.data(), &b);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready[(size_t)k] = b, mk_rc[(size_t)k] = rc, made[(size_t)k] = 1;
+                if (rc) mk_err[(size_t)k] = g_err;  // g_err is thread local
+            }
+            cv.notify_all();
+            if (rc) return;
         }
-        if (!rc) {
-            rc = kb_map_batch(ix, b, &res[(size_t)k]);
-            kb_batch_destroy(b);
-        }
-        rcs[(size_t)k] = rc;
-        if (rc) errs[(size_t)k] = g_err;  // g_err is thread local
-    };
-    if (n_slabs == 1) run_slab(0);
-    else {
-        std::atomic<int> next{0};
-        auto worker = [&]() {
-            for (int k; (k = next.fetch_add(1)) < n_slabs;) run_slab(k);
-        };
-        std::vector<std::thread> th;
-        int n_thr = 2;
-        if (const char *e = getenv("KAPTIVE_B200_SLAB_THREADS")) n_thr = atoi(e) > 0 ? atoi(e) : n_thr;
-        for (int t = 0; t < std::min(n_thr, n_slabs); ++t) th.emplace_back(worker);
-        for (auto &t : th) t.join();
-    }
+    });
     int rc = KB_OK;
-    int64_t tot_h = 0, tot_c = 0;
-    for (int k = 0; k < n_slabs; ++k) {
-        if (rcs[(size_t)k] && !rc) rc = fail(rcs[(size_t)k], errs[(size_t)k]);
-        if (res[(size_t)k]) tot_h += res[(size_t)k]->n_hits, tot_c += res[(size_t)k]->n_cigar;
-    }
-    if (!rc) {
-        if (n_hits) *n_hits = tot_h;
-        if (n_cigar) *n_cigar = tot_c;
-        if (dst) {
-            if (dst->capacity < tot_h) rc = fail(KB_ERR_CAPACITY, "hit arrays smaller than kb_result_size()");
-            else if (cigar && cigar_cap < tot_c) rc = fail(KB_ERR_CAPACITY, "cigar buffer smaller than kb_result_size()");
+    int64_t oh = 0, oc = 0;
+    bool cap_fail = false;
+    for (int k = 0; k < n_slabs && !rc; ++k) {
+        kb_batch_t *b = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return made[(size_t)k] != 0; });
+            b = ready[(size_t)k];
+            if (mk_rc[(size_t)k]) rc = fail(mk_rc[(size_t)k], mk_err[(size_t)k]);
         }
-    }
-    if (!rc && dst) {
-        int64_t oh = 0, oc = 0;
-        for (int k = 0; k < n_slabs && !rc; ++k) {
-            const kb_result_t *r = res[(size_t)k];
+        kb_result_t *r = nullptr;
+        if (!rc) rc = kb_map_batch(ix, b, &r);
+        if (b) kb_batch_destroy(b);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            consumed = k + 1;
+        }
+        cv.notify_all();
+        // too small: the remaining slabs are still mapped (not fetched) so that the sizes the caller needs for a retry are reported
+        if (!rc && dst && (dst->capacity < oh + r->n_hits || (cigar && cigar_cap < oc + r->n_cigar))) cap_fail = true;
+        if (!rc && dst && !cap_fail) {
             kb_hits_t v = *dst;  // a view of the caller's arrays starting at hit `oh`
             v.capacity = dst->capacity - oh;
 #define OFF(f) \
@@ -1047,10 +1074,23 @@ static int map_slabs(const kb_index_t *ix, const int32_t *asm_contig_start, int3
                     if (v.asm_id) v.asm_id[i] += a0;
                     if (v.cigar_off) v.cigar_off[i] += oc;
                 }
-            oh += r->n_hits, oc += r->n_cigar;
         }
+        if (r) oh += r->n_hits, oc += r->n_cigar;
+        kb_result_destroy(r);
     }
-    for (kb_result_t *r : res) kb_result_destroy(r);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cv.notify_all();
+    producer.join();
+    for (int k = 0; k < n_slabs; ++k)  // batches the producer made after a failure stopped the consumer
+        if (made[(size_t)k] && k >= consumed && ready[(size_t)k]) kb_batch_destroy(ready[(size_t)k]);
+    if (!rc) {
+        if (n_hits) *n_hits = oh;
+        if (n_cigar) *n_cigar = oc;
+        if (cap_fail) rc = fail(KB_ERR_CAPACITY, "hit arrays / cigar buffer smaller than the call's hits (sizes reported in n_hits / n_cigar)");
+    }
     return rc;
 }
 
@@ -1060,7 +1100,7 @@ int kb_map_assemblies(const kb_index_t *ix, const uint8_t *contig_seqs, const in
                       const int32_t *asm_contig_start, int32_t n_asm, kb_hits_t *dst, int64_t *n_hits, uint32_t *cigar,
                       int64_t cigar_cap, int64_t *n_cigar)
 {
-    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar,
+    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar, false,
                      [&](int a0, int a1, int c0, const int32_t *acs, kb_batch_t **b) {
                          return kb_batch_create(contig_seqs, contig_off + c0, contig_len + c0, acs, a1 - a0, ix->device, b);
                      });
@@ -1077,7 +1117,7 @@ int kb_map_assemblies_packed(const kb_index_t *ix, const uint32_t *seq2, const u
     int64_t storage = 0;
     if (kb_packed_layout(contig_len, n_ctg, soff.data(), &storage) != KB_OK) return fail(KB_ERR_ARG, "bad contig lengths");
     soff[(size_t)n_ctg] = storage - 128;
-    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar,
+    return map_slabs(ix, asm_contig_start, n_asm, dst, n_hits, cigar, cigar_cap, n_cigar, true,
                      [&](int a0, int a1, int c0, const int32_t *acs, kb_batch_t **b) {
                          return kb_batch_create_packed(seq2, nmask, soff[(size_t)c0], contig_len + c0, acs, a1 - a0, ix->device, b);
                      });

@@ -141,6 +141,26 @@ extern "C" int kb_packed_layout(const int32_t *contig_len, int64_t n_contigs, in
     return KB_OK;
 }
 
+// records of one FASTA buffer = '>' at the start of a line; memchr for the rare '>' instead of one call per 80-column line
+static int64_t kb_fasta_count_records(const uint8_t *data, int64_t n)
+{
+    int64_t rec = 0, i = 0;
+    while (i < n) {
+        const uint8_t *g = (const uint8_t *)memchr(data + i, '>', (size_t)(n - i));
+        if (!g) break;
+        const int64_t p = (int64_t)(g - data);
+        if (p == 0 || data[p - 1] == '\n') ++rec;
+        i = p + 1;
+    }
+    return rec;
+}
+extern "C" int kb_fasta_ingest_count_records(const uint8_t *const *data, const int64_t *n, int32_t n_files, int32_t n_threads, int64_t *n_records)
+{
+    if (n_files < 0 || (n_files > 0 && (!data || !n || !n_records))) return KB_ERR_ARG;
+    kb_parallel_files(n_files, n_threads, [&](int32_t i) { n_records[i] = kb_fasta_count_records(data[i], n[i]); });
+    return KB_OK;
+}
+
 // record lengths and names of one FASTA buffer (no copy): the pass between counting and packing
 static int kb_fasta_lengths(const uint8_t *data, int64_t n, int64_t max_records, int64_t *name_off, int32_t *name_len, int32_t *seq_len)
 {
@@ -213,8 +233,28 @@ __attribute__((target("avx2,bmi2"))) static inline void kb_codes32_avx2(const ui
     codes = _pext_u64(q[0], m) | _pext_u64(q[1], m) << 16 | _pext_u64(q[2], m) << 32 | _pext_u64(q[3], m) << 48;
 }
 
-template <bool FAST>
-static int kb_fasta_pack_one(const uint8_t *data, int64_t n, int64_t max_records, const int64_t *soff, const int32_t *seq_len, KbBitSink sink)
+// 32 bytes -> codes / validity as above plus the positions of '\n' in the vector
+__attribute__((target("avx2,bmi2"))) static inline void kb_codes32_nl_avx2(const uint8_t *s, uint64_t &codes, uint32_t &valid, uint32_t &nl)
+{
+    const __m256i x = _mm256_loadu_si256((const __m256i *)s);
+    nl = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('\n')));
+    const __m256i u = _mm256_and_si256(x, _mm256_set1_epi8((char)0xdf));
+    __m256i v = _mm256_cmpeq_epi8(u, _mm256_set1_epi8('A'));
+    v = _mm256_or_si256(v, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('C')));
+    v = _mm256_or_si256(v, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('G')));
+    v = _mm256_or_si256(v, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('T')));
+    v = _mm256_or_si256(v, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('U')));
+    valid = (uint32_t)_mm256_movemask_epi8(v);
+    const __m256i c1 = _mm256_srli_epi16(x, 1), c2 = _mm256_srli_epi16(x, 2);
+    const __m256i cd = _mm256_and_si256(_mm256_and_si256(_mm256_xor_si256(c1, c2), _mm256_set1_epi8(3)), v);
+    alignas(32) uint64_t q[4];
+    _mm256_store_si256((__m256i *)q, cd);
+    const uint64_t m = 0x0303030303030303ull;
+    codes = _pext_u64(q[0], m) | _pext_u64(q[1], m) << 16 | _pext_u64(q[2], m) << 32 | _pext_u64(q[3], m) << 48;
+}
+
+// portable form: line by line
+static int kb_fasta_pack_one_generic(const uint8_t *data, int64_t n, int64_t max_records, const int64_t *soff, KbBitSink sink)
 {
     int64_t rec = -1, i = 0, b = 0;
     while (i < n) {
@@ -227,29 +267,63 @@ static int kb_fasta_pack_one(const uint8_t *data, int64_t n, int64_t max_records
             int64_t len = e - i;
             while (len > 0 && (data[i + len - 1] == '\r' || data[i + len - 1] == ' ' || data[i + len - 1] == '\t')) --len;
             const uint8_t *s = data + i;
-            int64_t k = 0;
             uint64_t codes;
             uint32_t valid;
-            for (; k + 32 <= len; k += 32) {
-                if (FAST) kb_codes32_avx2(s + k, codes, valid);
-                else kb_codes32_generic(s + k, 32, codes, valid);
-                sink.put(b + k, codes, valid, 32);
-            }
-            if (k < len) {
-                kb_codes32_generic(s + k, (int)(len - k), codes, valid);
-                sink.put(b + k, codes, valid, (int)(len - k));
+            for (int64_t k = 0; k < len; k += 32) {
+                const int m = len - k < 32 ? (int)(len - k) : 32;
+                kb_codes32_generic(s + k, m, codes, valid);
+                sink.put(b + k, codes, valid, m);
             }
             b += len;
         }
         i = e + 1;
     }
-    (void)seq_len;
     return KB_OK;
 }
+// AVX2 + BMI2 form: the vector that yields the codes also finds the end of the line (no memchr per 80-column line)
 __attribute__((target("avx2,bmi2"))) static int kb_fasta_pack_one_fast(const uint8_t *data, int64_t n, int64_t max_records, const int64_t *soff,
-                                                                      const int32_t *seq_len, KbBitSink sink)
+                                                                      KbBitSink sink)
 {
-    return kb_fasta_pack_one<true>(data, n, max_records, soff, seq_len, sink);
+    int64_t rec = -1, i = 0, b = 0;
+    while (i < n) {
+        if (data[i] == '>') {  // header line
+            const uint8_t *nl = (const uint8_t *)memchr(data + i, '\n', (size_t)(n - i));
+            if (++rec >= max_records) return KB_ERR_CAPACITY;
+            b = soff[rec];
+            i = nl ? (int64_t)(nl - data) + 1 : n;
+            continue;
+        }
+        if (rec < 0) {  // text before the first header is ignored
+            const uint8_t *nl = (const uint8_t *)memchr(data + i, '\n', (size_t)(n - i));
+            i = nl ? (int64_t)(nl - data) + 1 : n;
+            continue;
+        }
+        // one sequence line starting at i
+        for (;;) {
+            uint64_t codes;
+            uint32_t valid, nlm;
+            int64_t len;  // bases of this vector that belong to the line
+            bool eol;
+            if (i + 32 <= n) {
+                kb_codes32_nl_avx2(data + i, codes, valid, nlm);
+                eol = nlm != 0;
+                len = eol ? (int64_t)__builtin_ctz(nlm) : 32;
+            } else {  // the last < 32 bytes of the buffer
+                const uint8_t *nl = (const uint8_t *)memchr(data + i, '\n', (size_t)(n - i));
+                len = nl ? (int64_t)(nl - (data + i)) : n - i;
+                eol = true;
+                kb_codes32_generic(data + i, (int)len, codes, valid);
+            }
+            int64_t keep = len;
+            if (eol)  // trailing blanks of the line are not sequence
+                while (keep > 0 && (data[i + keep - 1] == '\r' || data[i + keep - 1] == ' ' || data[i + keep - 1] == '\t')) --keep;
+            if (keep > 0) sink.put(b, codes, valid, (int)keep);
+            b += keep;
+            i += eol ? len + 1 : len;
+            if (eol || i >= n) break;
+        }
+    }
+    return KB_OK;
 }
 
 // pass 2 of the packed ingest: per-record lengths and names (rec_base from kb_fasta_ingest_count's counts)
@@ -297,8 +371,8 @@ extern "C" int kb_fasta_ingest_pack(const uint8_t *const *data, const int64_t *n
         if (i == n_files - 1) b1 = storage_bases;
         if (r0 == r1 && i != 0 && i != n_files - 1) b0 = b1;  // an empty file in the middle owns nothing
         if (b1 > b0) clear(b0, b1);
-        int r = fast ? kb_fasta_pack_one_fast(data[i], n[i], r1 - r0, contig_soff + r0, contig_len + r0, sink)
-                     : kb_fasta_pack_one<false>(data[i], n[i], r1 - r0, contig_soff + r0, contig_len + r0, sink);
+        int r = fast ? kb_fasta_pack_one_fast(data[i], n[i], r1 - r0, contig_soff + r0, sink)
+                     : kb_fasta_pack_one_generic(data[i], n[i], r1 - r0, contig_soff + r0, sink);
         if (r != KB_OK) rc = r;
     });
     if (n_files == 0) clear(0, storage_bases);

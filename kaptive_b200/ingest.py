@@ -113,8 +113,8 @@ def ingest_fasta_packed(files: list[bytes], threads: int | None = None, out: tup
     bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
     ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if len(b) else None for b in bufs])
     lens = np.array([len(b) for b in bufs], dtype=np.int64)
-    n_rec, n_seq = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.int64)
-    _lib.check(L.kb_fasta_ingest_count(ptrs, ptr(lens), n, threads, ptr(n_rec), ptr(n_seq)))
+    n_rec = np.zeros(max(n, 1), np.int64)
+    _lib.check(L.kb_fasta_ingest_count_records(ptrs, ptr(lens), n, threads, ptr(n_rec)))
     rec_base = np.concatenate([[0], np.cumsum(n_rec[:n])]).astype(np.int64)
     tot_r = int(rec_base[-1])
     ln = np.zeros(max(tot_r, 1), np.int32)

@@ -108,6 +108,17 @@ class AssemblyBatch:
         self.contig_lengths, self.asm_contig_start, self.contig_names = pb.contig_len, pb.asm_contig_start, pb.names
         return self
 
+    def download_packed(self, out: tuple[np.ndarray, np.ndarray] | None = None) -> tuple[np.ndarray, np.ndarray]:
+        """The batch's 2-bit words and mask words as host arrays (layout of ``kb_packed_layout`` over the batch's contigs)."""
+        L = _lib.load()
+        st = C.c_int64(0)
+        check(L.kb_batch_download_packed(self._h, None, None, C.byref(st)))
+        seq2, nmask = out if out is not None else (np.empty(st.value // 16, np.uint32), np.empty(st.value // 32, np.uint32))
+        if len(seq2) < st.value // 16 or len(nmask) < st.value // 32:
+            raise ValueError("buffers smaller than the batch's storage")
+        check(L.kb_batch_download_packed(self._h, ptr(seq2), ptr(nmask), None))
+        return seq2[: st.value // 16], nmask[: st.value // 32]
+
     @property
     def total_bases(self) -> int:
         return int(_lib.load().kb_batch_total_bases(self._h))
