@@ -232,6 +232,39 @@ int kb_post_cull_overlaps(const int32_t *order, const int32_t *group1, const int
 int kb_post_cluster(const int32_t *starts, const int32_t *ends, const int32_t *groups, int32_t tolerance, const int32_t *order,
                     const int64_t *seg_off, int32_t n_seg, int32_t *cluster_ids);
 
+/* ---- batched typing of mapped assemblies: the post-mapping part of Serotyper.__call__
+ * (src/kaptive/serotyping/core.py:157-486) for a whole batch.  Array logic on host threads, numerics (extract + translate +
+ * protein Gotoh of every retained hit) in one device pass over the resident packed batch.  Same tie rules as the reference. */
+typedef struct kb_typedb kb_typedb_t;
+typedef struct kb_typed kb_typed_t;
+const char *kb_type_last_error(void);
+/* one entry per database gene: db.genes.lengths, db.gene_locus_indices, db.extra_genes, db.gene_positions, db.gene_intervals.strands;
+ * locus_len = db.loci.lengths; translations = db.translations (bytes back to back, trans_len each); id_threshold = db.metadata.id_threshold */
+int kb_typedb_create(int32_t n_genes, const int32_t *gene_len, const int32_t *gene_locus, const uint8_t *extra, const int32_t *gene_pos,
+                     const int8_t *gene_strand, int32_t n_loci, const int32_t *locus_len, int32_t max_locus_length, const uint8_t *translations,
+                     const int32_t *trans_len, double id_threshold, int device, kb_typedb_t **out);
+void kb_typedb_destroy(kb_typedb_t *d);
+/* serotyping/core.py:163-201: locus_scores (n_asm x n_loci float64) and locus_counts (float32) from hits sorted by (assembly, gene);
+ * the caller finishes :199-206 (completeness ** 3, argmax) with numpy, whose float32 power the reference uses */
+int kb_type_score(const kb_typedb_t *d, const int32_t *asm_id, const int32_t *gene, const int32_t *q_start, const int32_t *q_end, const int32_t *score,
+                  int64_t n_hits, int32_t n_asm, double min_gene_coverage, int32_t n_threads, double *locus_scores, float *locus_counts);
+/* serotyping/core.py:209-459 for every assembly of `batch` given its best locus (and that locus' un-penalised score, :471) */
+int kb_type_call(const kb_typedb_t *d, const kb_batch_t *batch, const int32_t *asm_id, const int32_t *gene, const int32_t *q_start, const int32_t *q_end,
+                 const int32_t *t_ctg, const int32_t *t_len, const int32_t *t_start, const int32_t *t_end, const int8_t *strand, const int32_t *score,
+                 const int32_t *matches, const uint8_t *mapq, int64_t n_hits, int32_t n_asm, const int32_t *best_locus, const double *best_score,
+                 int32_t max_other_genes, double min_completeness, int32_t allow_below_threshold, int32_t partial_edge_tolerance, int32_t n_threads,
+                 kb_typed_t **out);
+void kb_typed_destroy(kb_typed_t *r);
+int kb_typed_sizes(const kb_typed_t *r, int64_t *n_gene_hits, int64_t *n_pieces, int64_t *n_missing);
+/* per assembly (offset arrays: n_asm + 1); problems: bit 0 fragmented, 1 unexpected genes, 2 missing genes, 3 novel genes, 4 truncated genes */
+int kb_typed_fetch_assemblies(const kb_typed_t *r, double *score, double *completeness, double *pcov, double *length_discrepancy, uint8_t *typeable,
+                              uint8_t *problems, int32_t *n_pieces, int64_t *gene_hit_off, int64_t *piece_off, int64_t *missing_off);
+/* gene hits in the reference's order (GeneHits after the spurious-hit filter); state: 0 normal, 1 partial, 2 truncated, 3 novel */
+int kb_typed_fetch_gene_hits(const kb_typed_t *r, int32_t *gene, int32_t *q_start, int32_t *q_end, int32_t *t_ctg, int32_t *t_start, int32_t *t_end,
+                             int8_t *strand, int8_t *state, uint8_t *is_expected, uint8_t *is_inside, uint8_t *is_extra, float *prot_ident,
+                             float *coverage);
+int kb_typed_fetch_pieces(const kb_typed_t *r, int32_t *ctg, int32_t *start, int32_t *end, int8_t *strand, int32_t *missing);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,17 @@ _SYMBOLS = [
     ("kb_map_assemblies_packed", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(KbHits), _P, _P, C.c_int64, _P]),
     ("kb_scan_minimizers", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     ("kb_bench_scan", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("kb_type_last_error", C.c_char_p, []),
+    ("kb_typedb_create", C.c_int, [C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, C.c_double, C.c_int, C.POINTER(_P)]),
+    ("kb_typedb_destroy", None, [_P]),
+    ("kb_type_score", C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_double, C.c_int32, _P, _P]),
+    ("kb_type_call", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, C.c_double,
+                               C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    ("kb_typed_destroy", None, [_P]),
+    ("kb_typed_sizes", C.c_int, [_P, _P, _P, _P]),
+    ("kb_typed_fetch_assemblies", C.c_int, [_P] * 11),
+    ("kb_typed_fetch_gene_hits", C.c_int, [_P] * 14),
+    ("kb_typed_fetch_pieces", C.c_int, [_P] * 6),
     ("kb_post_last_error", C.c_char_p, []),
     ("kb_post_extract", C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_int64, _P, _P]),
     ("kb_post_translate", C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P, _P, _P]),

@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "_lib" / "libkaptive_b200.so"
-SOURCES = ["kb_api.cu", "kb_scan.cu", "kb_pipeline.cu", "kb_post.cu", "kb_index.cpp", "kb_params.cpp", "kb_fasta.cpp"]
+SOURCES = ["kb_api.cu", "kb_scan.cu", "kb_pipeline.cu", "kb_post.cu", "kb_index.cpp", "kb_params.cpp", "kb_fasta.cpp", "kb_type.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "--extended-lambda", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wno-unknown-pragmas", "-shared",

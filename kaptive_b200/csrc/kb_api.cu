@@ -187,6 +187,14 @@ struct kb_result {
     std::vector<int32_t> chain_dump;
 };
 
+// internal: the device view of a batch for the typing numerics (kb_type.cpp)
+const KbBatchView *kb_batch_view_internal(const kb_batch *b, int *device)
+{
+    if (!b) return nullptr;
+    if (device) *device = b->device;
+    return &b->view;
+}
+
 static void setup_mempool(int device)
 {
     cudaMemPool_t mp;

@@ -229,6 +229,35 @@ __global__ void gotoh_kernel(const uint8_t *q, const int64_t *q_off, const int32
     int32_t *r = res + (int64_t)idx * 8;
     r[0] = max_score, r[1] = matches, r[2] = mismatches, r[3] = gaps, r[4] = i, r[5] = max_i, r[6] = j, r[7] = max_j;
 }
+
+// ---- typing numerics on the device-resident batch (kb_type.cpp): extract + translate fused, straight from the 2-bit packed
+// contigs.  Item i = bases [ts, te) of contig `ctg` (batch-global index), reverse-complemented when strand < 0, read in frame
+// `frame`, translated with table 11 up to the first stop codon (seq.py:612-741 fused; a base that is not A/C/G/T/U is code 4 in
+// the reference's char_map too, so the packed form loses nothing).  One thread per item; out at out_off[i], length to prot_len[i].
+__global__ void type_translate_kernel(KbBatchView bv, const int32_t *ctg, const int32_t *ts, const int32_t *te, const int8_t *strand,
+                                      const int8_t *frame, const int64_t *out_off, int64_t n, uint8_t *out, int32_t *prot_len)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t L = te[i] - ts[i], f = frame[i];
+    int32_t nc = 0;
+    if (L > f) {
+        const int32_t adj = L - f, mx = adj >= 3 ? adj / 3 : 0;
+        const int64_t base = bv.ctg_soff[ctg[i]];
+        const bool rev = strand[i] < 0;
+        uint8_t *o = out + out_off[i];
+        auto code = [&](int32_t x) {  // base x of the extracted (oriented) sequence
+            const int c = kb_fetch_base(bv.seq2, bv.nmask, rev ? base + te[i] - 1 - x : base + ts[i] + x);
+            return rev && c < 4 ? 3 - c : c;
+        };
+        for (int32_t x = f; nc < mx; ++nc, x += 3) {
+            const uint8_t aa = c_tab.codon[code(x) * 25 + code(x + 1) * 5 + code(x + 2)];
+            if (aa == 42) break;
+            o[nc] = aa;
+        }
+    }
+    prot_len[i] = nc;
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -456,3 +485,91 @@ int kb_post_cluster(const int32_t *starts, const int32_t *ends, const int32_t *g
 }
 
 }  // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Typing numerics for a batch (internal, called by kb_type.cpp): translate every item from the packed batch, then align each
+// protein with the database translation of its gene (banded local Gotoh, the kernel above).  Device-resident inputs (batch,
+// translations); items are processed in chunks so that the traceback scratch stays bounded.  prot_len: n; res: n x 8.
+int kb_post_type_numerics(const KbBatchView &bv, int device, const int32_t *ctg, const int32_t *ts, const int32_t *te, const int8_t *strand,
+                          const int8_t *frame, const int32_t *gene, int64_t n, const uint8_t *d_trans, const int64_t *d_trans_off,
+                          const int32_t *h_trans_len, int32_t k, int32_t go, int32_t ge, int32_t *prot_len,
+                          int32_t *res)
+{
+    if (n <= 0) return KB_OK;
+    try {
+        PCU(cudaSetDevice(device));
+        ensure_device();
+        const int64_t chunk = 1 << 18;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+            const int64_t m = n - c0 < chunk ? n - c0 : chunk;
+            Dev D;
+            std::vector<int64_t> aa_off((size_t)m);
+            int64_t aa_total = 0;
+            for (int64_t i = 0; i < m; ++i) {
+                const int32_t L = te[c0 + i] - ts[c0 + i];
+                aa_off[(size_t)i] = aa_total, aa_total += (L > 0 ? L / 3 : 0) + 1;
+            }
+            const int32_t *d_ctg = D.upload(ctg + c0, (size_t)m), *d_ts = D.upload(ts + c0, (size_t)m), *d_te = D.upload(te + c0, (size_t)m);
+            const int8_t *d_st = D.upload(strand + c0, (size_t)m), *d_fr = D.upload(frame + c0, (size_t)m);
+            const int64_t *d_ao = D.upload(aa_off.data(), (size_t)m);
+            uint8_t *d_aa = D.alloc<uint8_t>((size_t)aa_total);
+            int32_t *d_pl = D.alloc<int32_t>((size_t)m);
+            type_translate_kernel<<<(unsigned)((m + 127) / 128), 128>>>(bv, d_ctg, d_ts, d_te, d_st, d_fr, d_ao, m, d_aa, d_pl);
+            PCU(cudaGetLastError());
+            PCU(cudaMemcpy(prot_len + c0, d_pl, (size_t)m * 4, cudaMemcpyDeviceToHost));
+            // protein DP: query = the translated hit, target = the database translation of its gene
+            std::vector<int64_t> tb_off((size_t)m), row_off((size_t)m), t_off_sel((size_t)m);
+            std::vector<int32_t> t_len_sel((size_t)m);
+            int64_t tb_total = 0, row_total = 0;
+            for (int64_t i = 0; i < m; ++i) {
+                const int32_t l1 = prot_len[c0 + i], l2 = h_trans_len[gene[c0 + i]];
+                const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1, bw = 2 * kl + 3;
+                tb_off[(size_t)i] = tb_total, tb_total += ((int64_t)l1 + 1) * bw;
+                row_off[(size_t)i] = row_total, row_total += 4 * bw;
+                t_len_sel[(size_t)i] = l2;
+            }
+            const int64_t *d_tbo = D.upload(tb_off.data(), (size_t)m), *d_ro = D.upload(row_off.data(), (size_t)m);
+            const int32_t *d_tl = D.upload(t_len_sel.data(), (size_t)m);
+            int64_t *d_to = D.alloc<int64_t>((size_t)m);
+            // target offsets: the table is small (one entry per gene): fetch it and gather on the host
+            {
+                int32_t gmax = 0;
+                for (int64_t i = 0; i < m; ++i) gmax = gene[c0 + i] > gmax ? gene[c0 + i] : gmax;
+                std::vector<int64_t> table((size_t)gmax + 1), h_to((size_t)m);
+                PCU(cudaMemcpy(table.data(), d_trans_off, ((size_t)gmax + 1) * 8, cudaMemcpyDeviceToHost));
+                for (int64_t i = 0; i < m; ++i) h_to[(size_t)i] = table[(size_t)gene[c0 + i]];
+                PCU(cudaMemcpy(d_to, h_to.data(), (size_t)m * 8, cudaMemcpyHostToDevice));
+            }
+            uint8_t *d_tb = D.alloc<uint8_t>((size_t)tb_total);
+            int32_t *d_rows = D.alloc<int32_t>((size_t)row_total), *d_res = D.alloc<int32_t>((size_t)m * 8);
+            gotoh_kernel<<<(unsigned)((m + 63) / 64), 64>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)m, k, go, ge, d_tbo, d_tb, d_ro, d_rows, d_res);
+            PCU(cudaGetLastError());
+            PCU(cudaMemcpy(res + c0 * 8, d_res, (size_t)m * 32, cudaMemcpyDeviceToHost));
+        }
+    } catch (const std::string &) {
+        return KB_ERR_CUDA;
+    }
+    return KB_OK;
+}
+
+// small device-memory helpers for kb_type.cpp (host-only translation unit)
+void *kb_type_dev_upload(int device, const void *h, size_t bytes)
+{
+    void *d = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&d, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    if (h && bytes && cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return nullptr;
+    }
+    return d;
+}
+void kb_type_dev_free(int device, void *p)
+{
+    if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p);
+}
+int kb_type_dev_download(int device, void *h, const void *dptr, size_t bytes)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    return cudaMemcpy(h, dptr, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
