@@ -255,6 +255,8 @@ int kb_type_call(const kb_typedb_t *d, const kb_batch_t *batch, const int32_t *a
                  int32_t max_other_genes, double min_completeness, int32_t allow_below_threshold, int32_t partial_edge_tolerance, int32_t n_threads,
                  kb_typed_t **out);
 void kb_typed_destroy(kb_typed_t *r);
+/* diagnostic: seconds the last kb_type_call spent in pass 1 (host), building the job list, the device numerics, pass 2 (host) */
+void kb_type_debug_times(double *t4);
 int kb_typed_sizes(const kb_typed_t *r, int64_t *n_gene_hits, int64_t *n_pieces, int64_t *n_missing);
 /* per assembly (offset arrays: n_asm + 1); problems: bit 0 fragmented, 1 unexpected genes, 2 missing genes, 3 novel genes, 4 truncated genes */
 int kb_typed_fetch_assemblies(const kb_typed_t *r, double *score, double *completeness, double *pcov, double *length_discrepancy, uint8_t *typeable,

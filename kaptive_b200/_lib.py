@@ -102,6 +102,7 @@ _SYMBOLS = [
     ("kb_type_call", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, C.c_int32, C.c_double,
                                C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     ("kb_typed_destroy", None, [_P]),
+    ("kb_type_debug_times", None, [_P]),
     ("kb_typed_sizes", C.c_int, [_P, _P, _P, _P]),
     ("kb_typed_fetch_assemblies", C.c_int, [_P] * 11),
     ("kb_typed_fetch_gene_hits", C.c_int, [_P] * 14),

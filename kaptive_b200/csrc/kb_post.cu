@@ -13,6 +13,9 @@
 // parallelism, exactly as in the reference's prange.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "kb_common.cuh"
@@ -258,6 +261,91 @@ __global__ void type_translate_kernel(KbBatchView bv, const int32_t *ctg, const 
     }
     prot_len[i] = nc;
 }
+
+// ---- banded local Gotoh for the typing pass: the same recurrences and tie rules as gotoh_kernel, but the three numbers the
+// typing logic consumes (matches, mismatches, gaps of the traceback path) are carried FORWARD with every state instead of being
+// recovered from a stored traceback: a state's counts are those of the predecessor the reference's traceback would step to
+// (M <- diag / D / I by `tbm`, D <- M when d_open >= d_ext else D, I <- M when i_open >= i_ext else I), so the counts at the first
+// maximum cell are exactly what the traceback from that cell yields -- with two rows of state per pair and no traceback memory
+// (the stored form needs (len + 1) * band bytes per pair: 15 KB for a typical gene, several GB per batch).
+// counts packed as matches | mismatches << 21 | gaps << 42.  res: n x 4 = score, matches, mismatches, gaps.
+// Thread `tid` works on pair perm[tid] (pairs sorted by band width, so the lanes of a warp run rows of similar length); the row
+// state of a warp's 32 pairs is interleaved (element jm of lane l at tile + jm * 32 + l), which makes every access of the inner
+// loop one coalesced line per warp.
+__global__ void gotoh_counts_kernel(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t, const int64_t *t_off,
+                                    const int32_t *t_len, int32_t n, int32_t k, int32_t go, int32_t ge, const int32_t *perm, const int64_t *tile_off,
+                                    const int32_t *tile_bw, int32_t *rowbuf, unsigned long long *cntbuf, int32_t *res)
+{
+    // the substitution tables in shared memory: lanes index them with different residues, which a __constant__ bank serialises
+    __shared__ int8_t s_aa[256], s_bl[625];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_aa[x] = c_tab.aa_idx[x];
+    for (int x = threadIdx.x; x < 625; x += blockDim.x) s_bl[x] = c_tab.blosum[x];
+    __syncthreads();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const int idx = perm[tid];
+    const int64_t tile = tile_off[tid >> 5];
+    const int32_t tbw = tile_bw[tid >> 5], lane = tid & 31;
+    typedef unsigned long long u64;
+    const int32_t INF = -1000000000;
+    const u64 ONE_M = 1ull, ONE_X = 1ull << 21, ONE_G = 1ull << 42;
+    const uint8_t *s1 = q + q_off[idx], *s2 = t + t_off[idx];
+    const int32_t len1 = q_len[idx], len2 = t_len[idx], rows = len1 + 1, cols = len2 + 1;
+    const int32_t dl = len1 > len2 ? len1 - len2 : len2 - len1;
+    const int32_t kl = k > dl + 1 ? k : dl + 1, bw = 2 * kl + 3;
+    // four arrays of tbw x 32 elements each per warp tile; this lane's element jm sits at [jm * 32]
+    int32_t *Mp = rowbuf + tile * 4 + lane, *Dp = Mp + (int64_t)tbw * 32, *Mc = Dp + (int64_t)tbw * 32, *Dc = Mc + (int64_t)tbw * 32;
+    u64 *CMp = cntbuf + tile * 4 + lane, *CDp = CMp + (int64_t)tbw * 32, *CMc = CDp + (int64_t)tbw * 32, *CDc = CMc + (int64_t)tbw * 32;
+    int32_t max_score = 0;
+    u64 max_cnt = 0;
+    // no initialisation of the rows: every read below is guarded by the range the previous row actually computed ([psj, pej))
+    for (int32_t i = 1; i < rows; ++i) {
+        const int32_t sj = i - kl > 1 ? i - kl : 1, ej = i + kl + 1 < cols ? i + kl + 1 : cols;
+        const int32_t sp = i - 1 - kl - 1 > 0 ? i - 1 - kl - 1 : 0, sc = i - kl - 1 > 0 ? i - kl - 1 : 0;
+        if (sj < cols && ej > 1) {
+            const uint8_t a = s1[i - 1];
+            const int32_t ai = s_aa[a];
+            int32_t m_left = 0, i_left = INF;
+            u64 cm_left = 0, ci_left = 0;
+            const int32_t psj = i - 1 >= 1 ? (i - 1 - kl > 1 ? i - 1 - kl : 1) : cols, pej = i - 1 >= 1 ? (i + kl < cols ? i + kl : cols) : 0;
+            for (int32_t j = sj; j < ej; ++j) {
+                const bool top_ok = j >= psj && j < pej, tl_ok = j - 1 >= psj && j - 1 < pej;
+                const int32_t m_top = top_ok ? Mp[(j - sp) * 32] : 0, d_top = top_ok ? Dp[(j - sp) * 32] : INF, m_tl = tl_ok ? Mp[(j - 1 - sp) * 32] : 0;
+                const u64 cm_top = top_ok ? CMp[(j - sp) * 32] : 0, cd_top = top_ok ? CDp[(j - sp) * 32] : 0, cm_tl = tl_ok ? CMp[(j - 1 - sp) * 32] : 0;
+                const int32_t d_open = m_top - go - ge, d_ext = d_top - ge;
+                int32_t dcur, icur;
+                u64 cd, ci;
+                if (d_open >= d_ext) dcur = d_open, cd = cm_top + ONE_G;
+                else dcur = d_ext, cd = cd_top + ONE_G;
+                const int32_t i_open = m_left - go - ge, i_ext = i_left - ge;
+                if (i_open >= i_ext) icur = i_open, ci = cm_left + ONE_G;
+                else icur = i_ext, ci = ci_left + ONE_G;
+                const uint8_t b = s2[j - 1];
+                const int32_t bi = s_aa[b];
+                const int32_t sub = (ai >= 0 && bi >= 0) ? (int32_t)s_bl[ai * 25 + bi] : -128;
+                int32_t best = m_tl + sub;
+                u64 cb = cm_tl + (a == b ? ONE_M : ONE_X);
+                if (dcur > best) best = dcur, cb = cd;
+                if (icur > best) best = icur, cb = ci;
+                int32_t mcur;
+                u64 cm;
+                if (best <= 0) mcur = 0, cm = 0;
+                else {
+                    mcur = best, cm = cb;
+                    if (best > max_score) max_score = best, max_cnt = cb;
+                }
+                Mc[(j - sc) * 32] = mcur, Dc[(j - sc) * 32] = dcur, CMc[(j - sc) * 32] = cm, CDc[(j - sc) * 32] = cd;
+                m_left = mcur, i_left = icur, cm_left = cm, ci_left = ci;
+            }
+        }
+        int32_t *x = Mp;
+        Mp = Mc, Mc = x, x = Dp, Dp = Dc, Dc = x;
+        u64 *y = CMp;
+        CMp = CMc, CMc = y, y = CDp, CDp = CDc, CDc = y;
+    }
+    int32_t *r = res + (int64_t)idx * 4;
+    r[0] = max_score, r[1] = (int32_t)(max_cnt & 0x1fffff), r[2] = (int32_t)((max_cnt >> 21) & 0x1fffff), r[3] = (int32_t)(max_cnt >> 42);
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -493,64 +581,101 @@ int kb_post_cluster(const int32_t *starts, const int32_t *ends, const int32_t *g
 // translations); items are processed in chunks so that the traceback scratch stays bounded.  prot_len: n; res: n x 8.
 int kb_post_type_numerics(const KbBatchView &bv, int device, const int32_t *ctg, const int32_t *ts, const int32_t *te, const int8_t *strand,
                           const int8_t *frame, const int32_t *gene, int64_t n, const uint8_t *d_trans, const int64_t *d_trans_off,
-                          const int32_t *h_trans_len, int32_t k, int32_t go, int32_t ge, int32_t *prot_len,
-                          int32_t *res)
+                          const int32_t *h_trans_len, int32_t k, int32_t go, int32_t ge, int32_t *prot_len, int32_t *res)
 {
     if (n <= 0) return KB_OK;
+    if (n > 0x7fffffff) return KB_ERR_LIMIT;
+    cudaStream_t st = nullptr;
+    std::vector<void *> owned;
+    auto dalloc = [&](size_t bytes) {
+        void *p = nullptr;
+        PCU(cudaMallocAsync(&p, bytes ? bytes : 16, st));
+        owned.push_back(p);
+        return p;
+    };
+    auto up = [&](const void *h, size_t bytes) {
+        void *p = dalloc(bytes);
+        PCU(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st));
+        return p;
+    };
+    int rc = KB_OK;
+    const bool dbg = getenv("KAPTIVE_B200_DEBUG_TYPE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_0 = dbg ? now_ms() : 0;
     try {
         PCU(cudaSetDevice(device));
         ensure_device();
-        const int64_t chunk = 1 << 18;
-        for (int64_t c0 = 0; c0 < n; c0 += chunk) {
-            const int64_t m = n - c0 < chunk ? n - c0 : chunk;
-            Dev D;
-            std::vector<int64_t> aa_off((size_t)m);
-            int64_t aa_total = 0;
-            for (int64_t i = 0; i < m; ++i) {
-                const int32_t L = te[c0 + i] - ts[c0 + i];
-                aa_off[(size_t)i] = aa_total, aa_total += (L > 0 ? L / 3 : 0) + 1;
-            }
-            const int32_t *d_ctg = D.upload(ctg + c0, (size_t)m), *d_ts = D.upload(ts + c0, (size_t)m), *d_te = D.upload(te + c0, (size_t)m);
-            const int8_t *d_st = D.upload(strand + c0, (size_t)m), *d_fr = D.upload(frame + c0, (size_t)m);
-            const int64_t *d_ao = D.upload(aa_off.data(), (size_t)m);
-            uint8_t *d_aa = D.alloc<uint8_t>((size_t)aa_total);
-            int32_t *d_pl = D.alloc<int32_t>((size_t)m);
-            type_translate_kernel<<<(unsigned)((m + 127) / 128), 128>>>(bv, d_ctg, d_ts, d_te, d_st, d_fr, d_ao, m, d_aa, d_pl);
-            PCU(cudaGetLastError());
-            PCU(cudaMemcpy(prot_len + c0, d_pl, (size_t)m * 4, cudaMemcpyDeviceToHost));
-            // protein DP: query = the translated hit, target = the database translation of its gene
-            std::vector<int64_t> tb_off((size_t)m), row_off((size_t)m), t_off_sel((size_t)m);
-            std::vector<int32_t> t_len_sel((size_t)m);
-            int64_t tb_total = 0, row_total = 0;
-            for (int64_t i = 0; i < m; ++i) {
-                const int32_t l1 = prot_len[c0 + i], l2 = h_trans_len[gene[c0 + i]];
-                const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1, bw = 2 * kl + 3;
-                tb_off[(size_t)i] = tb_total, tb_total += ((int64_t)l1 + 1) * bw;
-                row_off[(size_t)i] = row_total, row_total += 4 * bw;
-                t_len_sel[(size_t)i] = l2;
-            }
-            const int64_t *d_tbo = D.upload(tb_off.data(), (size_t)m), *d_ro = D.upload(row_off.data(), (size_t)m);
-            const int32_t *d_tl = D.upload(t_len_sel.data(), (size_t)m);
-            int64_t *d_to = D.alloc<int64_t>((size_t)m);
-            // target offsets: the table is small (one entry per gene): fetch it and gather on the host
-            {
-                int32_t gmax = 0;
-                for (int64_t i = 0; i < m; ++i) gmax = gene[c0 + i] > gmax ? gene[c0 + i] : gmax;
-                std::vector<int64_t> table((size_t)gmax + 1), h_to((size_t)m);
-                PCU(cudaMemcpy(table.data(), d_trans_off, ((size_t)gmax + 1) * 8, cudaMemcpyDeviceToHost));
-                for (int64_t i = 0; i < m; ++i) h_to[(size_t)i] = table[(size_t)gene[c0 + i]];
-                PCU(cudaMemcpy(d_to, h_to.data(), (size_t)m * 8, cudaMemcpyHostToDevice));
-            }
-            uint8_t *d_tb = D.alloc<uint8_t>((size_t)tb_total);
-            int32_t *d_rows = D.alloc<int32_t>((size_t)row_total), *d_res = D.alloc<int32_t>((size_t)m * 8);
-            gotoh_kernel<<<(unsigned)((m + 63) / 64), 64>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)m, k, go, ge, d_tbo, d_tb, d_ro, d_rows, d_res);
-            PCU(cudaGetLastError());
-            PCU(cudaMemcpy(res + c0 * 8, d_res, (size_t)m * 32, cudaMemcpyDeviceToHost));
+        PCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        std::vector<int64_t> aa_off((size_t)n), t_off((size_t)n), row_off((size_t)n);
+        std::vector<int32_t> t_len((size_t)n);
+        int64_t aa_total = 0;
+        int32_t gmax = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t L = te[i] - ts[i];
+            aa_off[(size_t)i] = aa_total, aa_total += (L > 0 ? L / 3 : 0) + 1;
+            gmax = gene[i] > gmax ? gene[i] : gmax;
+        }
+        std::vector<int64_t> table((size_t)gmax + 2);
+        PCU(cudaMemcpyAsync(table.data(), d_trans_off, ((size_t)gmax + 2) * 8, cudaMemcpyDeviceToHost, st));
+        const int32_t *d_ctg = (const int32_t *)up(ctg, (size_t)n * 4), *d_ts = (const int32_t *)up(ts, (size_t)n * 4), *d_te = (const int32_t *)up(te, (size_t)n * 4);
+        const int8_t *d_st = (const int8_t *)up(strand, (size_t)n), *d_fr = (const int8_t *)up(frame, (size_t)n);
+        const int64_t *d_ao = (const int64_t *)up(aa_off.data(), (size_t)n * 8);
+        uint8_t *d_aa = (uint8_t *)dalloc((size_t)aa_total);
+        int32_t *d_pl = (int32_t *)dalloc((size_t)n * 4);
+        type_translate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bv, d_ctg, d_ts, d_te, d_st, d_fr, d_ao, n, d_aa, d_pl);
+        PCU(cudaGetLastError());
+        PCU(cudaMemcpyAsync(prot_len, d_pl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        PCU(cudaStreamSynchronize(st));  // the band of every pair depends on the length of its translated hit
+        const double t_tr = dbg ? now_ms() : 0;
+        // pairs sorted by band width (widest first); a warp's tile is as wide as its widest pair
+        std::vector<int32_t> bwv((size_t)n), perm((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t l1 = prot_len[i], l2 = h_trans_len[gene[i]];
+            const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1;
+            // a pair's rows are min(band, work) wide at most; its cost is rows x band: sort key = band, ties by query length
+            bwv[(size_t)i] = (int32_t)(2 * kl + 3);
+            t_len[(size_t)i] = l2, t_off[(size_t)i] = table[(size_t)gene[i]];
+            perm[(size_t)i] = (int32_t)i;
+        }
+        std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) {
+            if (bwv[(size_t)x] != bwv[(size_t)y]) return bwv[(size_t)x] > bwv[(size_t)y];
+            return prot_len[x] > prot_len[y];
+        });
+        const int64_t n_warp = (n + 31) / 32;
+        std::vector<int64_t> tile_off((size_t)n_warp);
+        std::vector<int32_t> tile_bw((size_t)n_warp);
+        int64_t row_total = 0;  // in elements of one array
+        for (int64_t w = 0; w < n_warp; ++w) {
+            tile_bw[(size_t)w] = bwv[(size_t)perm[(size_t)(w * 32)]];
+            tile_off[(size_t)w] = row_total, row_total += (int64_t)tile_bw[(size_t)w] * 32;
+        }
+        (void)row_off;
+        const int64_t *d_to = (const int64_t *)up(t_off.data(), (size_t)n * 8), *d_tile = (const int64_t *)up(tile_off.data(), (size_t)n_warp * 8);
+        const int32_t *d_tl = (const int32_t *)up(t_len.data(), (size_t)n * 4), *d_perm = (const int32_t *)up(perm.data(), (size_t)n * 4);
+        const int32_t *d_tbw = (const int32_t *)up(tile_bw.data(), (size_t)n_warp * 4);
+        int32_t *d_rows = (int32_t *)dalloc((size_t)row_total * 4 * 4), *d_res = (int32_t *)dalloc((size_t)n * 16);
+        unsigned long long *d_cnt = (unsigned long long *)dalloc((size_t)row_total * 4 * 8);
+        const double t_prep = dbg ? now_ms() : 0;
+        gotoh_counts_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)n, k, go, ge, d_perm, d_tile, d_tbw,
+                                                                     d_rows, d_cnt, d_res);
+        PCU(cudaGetLastError());
+        std::vector<int32_t> r4((size_t)n * 4);
+        PCU(cudaMemcpyAsync(r4.data(), d_res, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        PCU(cudaStreamSynchronize(st));
+        if (dbg)
+            fprintf(stderr, "[type numerics] %lld pairs: translate %.1f ms, host prep %.1f ms, gotoh %.1f ms (rows %.1f MB)\n", (long long)n, t_tr - t_0,
+                    t_prep - t_tr, now_ms() - t_prep, (double)row_total * 48 / 1e6);
+        for (int64_t i = 0; i < n; ++i) {  // the n x 8 layout of kb_post_protein_align; coordinates are not produced here
+            int32_t *o = res + i * 8;
+            o[0] = r4[(size_t)i * 4], o[1] = r4[(size_t)i * 4 + 1], o[2] = r4[(size_t)i * 4 + 2], o[3] = r4[(size_t)i * 4 + 3];
+            o[4] = o[5] = o[6] = o[7] = -1;
         }
     } catch (const std::string &) {
-        return KB_ERR_CUDA;
+        rc = KB_ERR_CUDA;
     }
-    return KB_OK;
+    for (void *p : owned) cudaFreeAsync(p, st);
+    if (st) cudaStreamSynchronize(st), cudaStreamDestroy(st);
+    return rc;
 }
 
 // small device-memory helpers for kb_type.cpp (host-only translation unit)

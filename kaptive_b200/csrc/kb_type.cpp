@@ -30,6 +30,9 @@ void *kb_type_dev_upload(int device, const void *h, size_t bytes);
 void kb_type_dev_free(int device, void *p);
 int kb_type_dev_download(int device, void *h, const void *dptr, size_t bytes);
 
+#include <chrono>
+static double g_type_times[4] = {0, 0, 0, 0};  // last kb_type_call: pass 1, job list, device numerics, pass 2 + assembly (seconds)
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static thread_local std::string g_type_err;
 static int tfail(int code, const std::string &m)
 {
@@ -211,6 +214,7 @@ int kb_type_call(const kb_typedb *d, const kb_batch *batch, const int32_t *asm_i
     if (kb_type_dev_download(device, acs.data(), bv->asm_ctg_start, ((size_t)n_asm + 1) * 4)) return tfail(KB_ERR_CUDA, "D2H of the contig table failed");
 
     // ------------------------------------------------------------ pass 1: cull, cluster, pieces, inside / missing
+    const double tm0 = now_s();
     parallel_for(n_asm, n_threads, [&](int64_t a) {
         AsmWork &w = W[(size_t)a];
         const int64_t lo = seg[(size_t)a], n = seg[(size_t)a + 1] - lo;
@@ -338,6 +342,7 @@ int kb_type_call(const kb_typedb *d, const kb_batch *batch, const int32_t *asm_i
     });
 
     // ------------------------------------------------------------ device pass: translate + protein alignment of every retained hit
+    const double tm1 = now_s();
     int64_t n_jobs = 0;
     for (int32_t a = 0; a < n_asm; ++a) W[(size_t)a].job0 = n_jobs, n_jobs += (int64_t)W[(size_t)a].idx.size();
     std::vector<int32_t> j_ctg((size_t)n_jobs), j_ts((size_t)n_jobs), j_te((size_t)n_jobs), j_gene((size_t)n_jobs), prot_len((size_t)n_jobs), res((size_t)n_jobs * 8);
@@ -352,11 +357,13 @@ int kb_type_call(const kb_typedb *d, const kb_batch *batch, const int32_t *asm_i
             j_frame[(size_t)j] = (int8_t)(((-(int64_t)q_start[h]) % 3 + 3) % 3);  // GeneHits.frames: (-q_starts) % 3 (Python modulo)
         }
     });
+    const double tm2 = now_s();
     if (int rc = kb_post_type_numerics(*bv, device, j_ctg.data(), j_ts.data(), j_te.data(), j_strand.data(), j_frame.data(), j_gene.data(), n_jobs, d->d_trans,
                                        d->d_trans_off, d->trans_len.data(), 20, 11, 1, prot_len.data(), res.data()))
         return tfail(rc, "typing numerics failed on the device");
 
     // ------------------------------------------------------------ pass 2: gene states, confidence, problems
+    const double tm3 = now_s();
     kb_typed *R = new kb_typed();
     R->n_asm = n_asm;
     R->score.resize((size_t)n_asm), R->completeness.resize((size_t)n_asm), R->pcov.resize((size_t)n_asm), R->length_discrepancy.resize((size_t)n_asm);
@@ -438,9 +445,12 @@ int kb_type_call(const kb_typedb *d, const kb_batch *batch, const int32_t *asm_i
             R->piece_ctg[po] = w.piece_ctg[i], R->piece_start[po] = w.piece_start[i], R->piece_end[po] = w.piece_end[i], R->piece_strand[po] = w.piece_strand[i];
         std::copy(w.missing.begin(), w.missing.end(), R->missing.begin() + R->miss_off[(size_t)a]);
     });
+    g_type_times[0] = tm1 - tm0, g_type_times[1] = tm2 - tm1, g_type_times[2] = tm3 - tm2, g_type_times[3] = now_s() - tm3;
     *out = R;
     return KB_OK;
 }
+// diagnostic: seconds spent by the last kb_type_call in pass 1 / job list / device numerics / pass 2
+void kb_type_debug_times(double *t4) { memcpy(t4, g_type_times, sizeof(g_type_times)); }
 
 void kb_typed_destroy(kb_typed *r) { delete r; }
 int kb_typed_sizes(const kb_typed *r, int64_t *n_gene_hits, int64_t *n_pieces, int64_t *n_missing)

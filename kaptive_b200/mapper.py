@@ -98,13 +98,15 @@ class AssemblyBatch:
         return batch
 
     @classmethod
-    def from_packed(cls, pb, device: int = 0) -> "AssemblyBatch":
-        """Host-packed contigs (``ingest.ingest_fasta_packed``) -> device batch: the 2-bit words go over PCIe as they are."""
+    def from_packed(cls, pb, device: int = 0, first_soff: int = 128) -> "AssemblyBatch":
+        """Host-packed contigs (``ingest.ingest_fasta_packed``) -> device batch: the 2-bit words go over PCIe as they are.
+        ``first_soff``: storage offset (bases) of the first contig of ``pb.contig_len`` inside ``pb.seq2`` / ``pb.nmask`` when ``pb`` is a
+        slice of a larger ingest call."""
         L = _lib.load()
         self = cls.__new__(cls)
         self.device, self.n_asm, self._h = device, len(pb.asm_contig_start) - 1, C.c_void_p(0)
-        check(L.kb_batch_create_packed(ptr(pb.seq2), ptr(pb.nmask), 128, ptr(pb.contig_len), ptr(pb.asm_contig_start), self.n_asm, device,
-                                       C.byref(self._h)))
+        check(L.kb_batch_create_packed(ptr(pb.seq2), ptr(pb.nmask), int(first_soff), ptr(pb.contig_len), ptr(pb.asm_contig_start), self.n_asm,
+                                       device, C.byref(self._h)))
         self.contig_lengths, self.asm_contig_start, self.contig_names = pb.contig_len, pb.asm_contig_start, pb.names
         return self
 

@@ -231,3 +231,55 @@ def type_many(db: TypingDB, batch, res, max_other_genes: int = 1, min_completene
                       length_discrepancy=ld[:n_asm], typeable=typeable[:n_asm].astype(bool), problems=problems[:n_asm], n_pieces=n_pieces[:n_asm],
                       gene_hit_off=gho, piece_off=pco, missing_off=mso, gene_hits={k: v[: ng.value] for k, v in g.items()},
                       pieces={k: v[: npc.value] for k, v in pc.items()}, missing=missing[: nm.value])
+
+
+def slab_bounds(n_asm: int, first: int = 512, second: int = 1536, big: int = 2560) -> list[int]:
+    """The slab plan of the packed host-buffer path (kb_api.cu:map_slabs): a short first slab so that little copy time is exposed,
+    then slabs as large as possible."""
+    if n_asm < 1024:
+        return [0, n_asm]
+    b = [0, min(first, n_asm // 4)]
+    if n_asm - b[-1] > 2 * second:
+        b.append(b[-1] + second)
+    base, rest = b[-1], n_asm - b[-1]
+    n = (rest + big - 1) // big
+    each = (rest + n - 1) // n
+    b += [min(n_asm, base + k * each) for k in range(1, n + 1)]
+    return b
+
+
+def type_packed(gi, db: TypingDB, pb, device: int = 0, threads: int | None = None, bounds: list[int] | None = None, **params) -> list[TypedBatch]:
+    """End-to-end typed path from host-packed assemblies (``ingest.ingest_fasta_packed``): slabs are copied to the device by a
+    producer thread (at most two ahead), mapped and typed in order.  Returns one :class:`TypedBatch` per slab (assembly order)."""
+    import queue
+    import threading
+
+    from . import ingest, mapper
+
+    bnd = bounds or slab_bounds(len(pb.asm_contig_start) - 1)
+    q: queue.Queue = queue.Queue(maxsize=2)
+
+    def produce():
+        try:
+            for k in range(len(bnd) - 1):
+                a0, a1 = bnd[k], bnd[k + 1]
+                c0, c1 = int(pb.asm_contig_start[a0]), int(pb.asm_contig_start[a1])
+                sub = ingest.PackedBatch(pb.seq2, pb.nmask, pb.contig_len[c0:c1], pb.contig_soff[c0:c1],
+                                         np.ascontiguousarray(pb.asm_contig_start[a0 : a1 + 1] - c0), pb.storage_bases, [])
+                first = int(pb.contig_soff[c0]) if c1 > c0 else 128
+                q.put(mapper.AssemblyBatch.from_packed(sub, device=device, first_soff=first))
+        except BaseException as e:  # noqa: BLE001  (handed to the consumer)
+            q.put(e)
+
+    th = threading.Thread(target=produce, daemon=True)
+    th.start()
+    out = []
+    for _ in range(len(bnd) - 1):
+        b = q.get()
+        if isinstance(b, BaseException):
+            raise b
+        res = gi.map(b)
+        out.append(type_many(db, b, res, threads=threads, **params))
+        b.close()
+    th.join()
+    return out

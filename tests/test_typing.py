@@ -59,6 +59,7 @@ def test_type_many_equals_the_unmodified_reference_pipeline():
     batch = mapper.AssemblyBatch.from_contigs([[s for _, s in a.contigs] for a in asms])
     res = gi.map(batch)
     tdb = serotype.TypingDB.from_synth(db)
+    tdb.kaptive_version = "unknown"  # what kaptive.__version__ says when the reference runs from its source tree (the golden run)
     assert [t for t in _translations_py(db)] == [bytes(x) for x in _trans_of(tdb, db)]
     typed = serotype.type_many(tdb, batch, res, threads=4)
     assert len(typed) == len(asms)
@@ -85,6 +86,28 @@ def test_type_many_equals_the_unmodified_reference_pipeline():
         assert typed.row(ai, a.name).decode() == g["row"], a.name
         n_rows += 1
     assert n_rows == 48 and sum(1 for a in asms if GOLD[a.name]["typeable"]) > 30
+
+
+@pytest.mark.gpu
+def test_type_packed_from_fasta_bytes_in_slabs_equals_type_many():
+    """FASTA bytes -> host-packed buffers -> type_packed (three slabs, producer thread) gives the calls of one type_many over the batch."""
+    import cases
+    from kaptive_b200 import ingest, mapper, serotype
+
+    db, n_k, n_o = tc.make_db()
+    asms = tc.make_assemblies(db, n_k, n_o)[:20]
+    gi = mapper.GeneIndex(db.genes)
+    tdb = serotype.TypingDB.from_synth(db)
+    tdb.kaptive_version = "unknown"
+    pb = ingest.ingest_fasta_packed([cases.fasta_bytes(a.contigs) for a in asms], threads=3)
+    parts = serotype.type_packed(gi, tdb, pb, bounds=[0, 3, 11, 20], threads=2)
+    assert [len(p) for p in parts] == [3, 8, 9]
+    k = 0
+    for p in parts:
+        for a in range(len(p)):
+            g = GOLD[asms[k].name]
+            assert p.row(a, asms[k].name).decode() == g["row"], asms[k].name
+            k += 1
 
 
 def _trans_of(tdb, db):
