@@ -270,7 +270,7 @@ int kb_index_create(const uint8_t *gene_seqs, const int64_t *offsets, const int3
 {
     if (!out || !params || (n_genes > 0 && (!gene_seqs || !offsets || !lengths))) return fail(KB_ERR_ARG, "null argument");
     if (params->max_gap >= KB_CTG_VGAP - 64 || params->bw >= KB_CTG_VGAP - 64) return fail(KB_ERR_LIMIT, "max_gap/bw must stay below 8128");
-    if (params->max_sw_cells <= 0 || params->max_sw_cells > 64000000) return fail(KB_ERR_LIMIT, "max_sw_cells out of range");
+    if (params->max_sw_cells <= 0 || params->max_sw_cells > 100000000) return fail(KB_ERR_LIMIT, "max_sw_cells out of range (1 .. 100,000,000 = minimap2 max_sw_mat)");
     kb_index *ix = new kb_index();
     std::string err = ix->host.build(gene_seqs, offsets, lengths, n_genes, *params);
     if (!err.empty()) {
@@ -729,18 +729,33 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         int64_t pool_cap = raw_cap * 24 + (1 << 16);
         int64_t n_raw = 0, n_pool = 0;
         uint32_t *pool = nullptr;
-        size_t sbytes = kb_align_scratch_bytes(p.max_sw_cells);
+        // Two scratch sizes.  The staged kernels (and the thousands of warps they keep resident) work with DP problems of up to
+        // KB_FAST_SW_CELLS cells -- all but a handful; a chain with a larger problem (minimap2 allows max_sw_mat = 100 M cells: an end
+        // extension over >= 1.4 kb of unaligned gene) is handed to the one-warp-per-chain kernel, which gets a few warps with scratch
+        // for the full p.max_sw_cells, allocated only when such a chain exists.
+        const int64_t KB_FAST_SW_CELLS = 4000000;
+        const int32_t fast_cells = (int32_t)std::min<int64_t>(p.max_sw_cells, KB_FAST_SW_CELLS);
+        KbIndexView iv_fast = iv;
+        iv_fast.p.max_sw_cells = fast_cells;
+        const size_t sbytes = kb_align_scratch_bytes(fast_cells), sbytes_full = kb_align_scratch_bytes(p.max_sw_cells);
         int n_warps = bt->n_sm * 24;  // resident warps of the DP kernels (6 CTAs of 4 warps per SM)
         {
             int64_t need_warps = ((n_chains + 3) / 4) * 4;
             if (need_warps < 4) need_warps = 4;
             if (n_warps > need_warps) n_warps = (int)need_warps;
         }
-        uint8_t *scratch = P.get<uint8_t>((size_t)n_warps * sbytes);
+        auto slow_warps_for = [&](int64_t n_slow) {  // warps of the full-size kernel: at most 8 GB of scratch, at least one CTA
+            int64_t w = std::max<int64_t>(4, ((int64_t)8 << 30) / (int64_t)sbytes_full / 4 * 4);
+            w = std::min<int64_t>(w, std::max<int64_t>(4, (n_slow + 3) / 4 * 4));
+            return (int)std::min<int64_t>(w, n_warps);
+        };
         unsigned long long *d_next = P.get<unsigned long long>(1);
         // staged path (kb_stage.cuh): plan -> band / rows DP kernels -> assemble; what it hands back goes to kb_align_kernel
         const char *sg = getenv("KAPTIVE_B200_STAGED");
         const bool staged = !(sg && sg[0] == '0') && n_chains > 0;
+        if (!staged) n_warps = slow_warps_for(n_chains);  // every chain goes through the full-size kernel
+        uint8_t *scratch = P.get<uint8_t>((size_t)n_warps * (staged ? sbytes : sbytes_full));
+        uint8_t *slow_scratch = nullptr;
         const int64_t job_cap = n_chains * 12 + 4096, jobcig_cap = job_cap * 16;
         int band_warps = bt->n_sm * 24, rows_warps = n_warps;
         if (const char *e = getenv("KAPTIVE_B200_BAND_WARPS")) band_warps = bt->n_sm * atoi(e);
@@ -771,19 +786,29 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             CU(cudaMemsetAsync(d_counters + 32, 0, 8 * 8, st));
             if (staged) {
                 CU(cudaMemsetAsync(r16_key, 0, (size_t)job_cap * 4, st));
-                kb_launch_stage_plan(iv, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, job_cap, band_list, rows_list, r16_list,
+                kb_launch_stage_plan(iv_fast, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, job_cap, band_list, rows_list, r16_list,
                                      r16_key, slow_list, d_counters, st);
-                kb_launch_stage_dp(iv, bv, jobs, band_list, rows_list, r16_list, r16_key, r16_list2, r16_key2, r16_tmp, r16_tmp_bytes,
+                kb_launch_stage_dp(iv_fast, bv, jobs, band_list, rows_list, r16_list, r16_key, r16_list2, r16_key2, r16_tmp, r16_tmp_bytes,
                                    band_scratch, band_warps, scratch, sbytes, rows_warps, jobcig, jobcig_cap, d_counters, st);
-                kb_launch_stage_assemble(iv, bv, chains, n_chains, ginfo, plans, jobs, jobcig, tmpcig, jobcig_cap + n_chains, raw, raw_cap, pool,
+                kb_launch_stage_assemble(iv_fast, bv, chains, n_chains, ginfo, plans, jobs, jobcig, tmpcig, jobcig_cap + n_chains, raw, raw_cap, pool,
                                          pool_cap, slow_list, d_counters, st);
-                kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next,
-                                slow_list, d_counters + 12, st);
-                launches += 9;
-            } else
-                kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next,
+                launches += 8;
+                // chains handed back (a DP problem over the fast limit, a z-drop inside a gap fill, a capacity limit): full-size kernel
+                unsigned long long n_slow = 0;
+                CU(cudaMemcpyAsync(&n_slow, d_counters + 12, 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (n_slow > 0) {
+                    const int sw = slow_warps_for((int64_t)n_slow);
+                    if (!slow_scratch) CU(cudaMallocAsync((void **)&slow_scratch, (size_t)sw * sbytes_full, st));
+                    kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, slow_scratch, sbytes_full, sw, raw, raw_cap, pool, pool_cap, d_counters,
+                                    d_next, slow_list, d_counters + 12, st);
+                    ++launches;
+                }
+            } else {
+                kb_launch_align(iv, bv, chains, n_chains, ginfo, cx, cy, scratch, sbytes_full, n_warps, raw, raw_cap, pool, pool_cap, d_counters, d_next,
                                 nullptr, nullptr, st);
-            ++launches;
+                ++launches;
+            }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(hc, d_counters, KB_N_COUNTERS * 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -798,6 +823,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         R->pool = pool, R->owned.push_back(pool), R->n_cigar = n_pool;
         R->counters[7] = (int64_t)hc[12];  // chains the staged path handed back to kb_align_kernel
         P.release(scratch);
+        if (slow_scratch) CU(cudaFreeAsync(slow_scratch, st));
         if (staged) {
             P.release(plans), P.release(jobs), P.release(band_list), P.release(rows_list), P.release(r16_list), P.release(slow_list), P.release(kscratch);
             P.release(r16_list2), P.release(r16_key), P.release(r16_key2), P.release(r16_tmp);

@@ -20,6 +20,6 @@ extern "C" void kb_params_default(kb_params_t *p)
     p->mask_len = INT_MAX;
     p->seed = 11;
     p->ext_bw = (int)(500 * 1.5 + 1.);
-    p->max_sw_cells = 4000000;
+    p->max_sw_cells = 100000000;  // minimap2 max_sw_mat
 }
 extern "C" void kbe_params_default(kb_params_t *p) { kb_params_default(p); }

@@ -757,6 +757,9 @@ extern "C" int kb_debug_dp(const kb_params_t *pp, int device, const uint8_t *q, 
     int64_t qb = 0, tbts = 0;
     for (int i = 0; i < n; ++i) qb = std::max<int64_t>(qb, qoff[i] + qlen[i]), tbts = std::max<int64_t>(tbts, toff[i] + tlen[i]);
     const int n_warps = 148 * 4;
+    kb_params_t fastp = *pp;  // the register-resident kernels work within the fast limit of the mapping path (kb_api.cu)
+    if (fastp.max_sw_cells > 4000000) fastp.max_sw_cells = 4000000;
+    pp = &fastp;
     const size_t sbytes = kb_align_scratch_bytes(pp->max_sw_cells);
     uint8_t *dq = nullptr, *dt = nullptr, *scr = nullptr;
     int64_t *dqo = nullptr, *dto = nullptr;

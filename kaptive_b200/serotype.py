@@ -271,15 +271,26 @@ def type_packed(gi, db: TypingDB, pb, device: int = 0, threads: int | None = Non
         except BaseException as e:  # noqa: BLE001  (handed to the consumer)
             q.put(e)
 
+    from concurrent.futures import ThreadPoolExecutor
+
     th = threading.Thread(target=produce, daemon=True)
     th.start()
-    out = []
-    for _ in range(len(bnd) - 1):
-        b = q.get()
-        if isinstance(b, BaseException):
-            raise b
-        res = gi.map(b)
-        out.append(type_many(db, b, res, threads=threads, **params))
-        b.close()
+    futs = []
+    # three stages in flight: the producer copies slab k + 2, this thread maps slab k + 1, the typing worker types slab k (host
+    # threads + one short device pass that shares the GPU with the mapping kernels)
+    with ThreadPoolExecutor(1) as typer:
+        def type_and_close(b, res):
+            try:
+                return type_many(db, b, res, threads=threads, **params)
+            finally:
+                b.close()
+
+        for _ in range(len(bnd) - 1):
+            b = q.get()
+            if isinstance(b, BaseException):
+                raise b
+            res = gi.map(b)
+            futs.append(typer.submit(type_and_close, b, res))
+        out = [f.result() for f in futs]
     th.join()
     return out

@@ -42,7 +42,7 @@ void kbo_params_default(kbo_params_t *p) /* [mm2:options.c:mm_idxopt_init/mm_map
     p->mask_len = INT_MAX;
     p->seed = 11;
     p->ext_bw = (int)(500 * 1.5 + 1.);
-    p->max_sw_cells = 4000000;
+    p->max_sw_cells = 100000000; /* [mm2:options.c:mm_mapopt_init] max_sw_mat */
 }
 
 /* ------------------------------------------------------- deterministic math */

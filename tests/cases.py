@@ -161,6 +161,23 @@ def case_long_contig_boundaries():
     return db, contigs
 
 
+def case_long_tail():
+    """A 4.2 kb gene of which only the first 2.3 kb are in the assembly (the rest of the contig is unrelated sequence): no seed beyond,
+    so the right end extension is a 1.9 k x 3.8 k rectangle (7.2 M cells) -- over the 4 M cells the staged DP kernels keep scratch for,
+    under minimap2's max_sw_mat of 100 M: the chain has to go through the full-size kernel, and the extension it finds (a few bases
+    into the unrelated sequence) must be the oracle's, not "skipped" (max_sw_cells)."""
+    rng = np.random.default_rng(77)
+    gene = synth.random_orf(rng, 1400)
+    db = small_db()
+    db = synth.SynthDB(genes=db.genes + [gene.tobytes()], gene_locus=np.append(db.gene_locus, db.gene_locus.max() + 1).astype(np.int32),
+                       gene_pos=np.append(db.gene_pos, 1).astype(np.int32), gene_start=np.append(db.gene_start, 0).astype(np.int32),
+                       gene_end=np.append(db.gene_end, len(gene)).astype(np.int32), gene_strand=np.append(db.gene_strand, 1).astype(np.int8),
+                       extra=np.append(db.extra, False), loci=db.loci + [gene.tobytes()], locus_names=db.locus_names + ["KLlong"],
+                       gene_names=db.gene_names + ["KLlong_01_glong"])
+    head = synth.mutate(rng, gene[:2300], 0.01)
+    return db, _custom(78, [head], spacer=9000)
+
+
 CASES = {
     "exact": case_exact,
     "mutated0": lambda: case_mutated(0),
@@ -179,6 +196,7 @@ CASES = {
     "empty_assembly": case_empty_assembly,
     "no_locus": case_no_locus,
     "boundaries": case_long_contig_boundaries,
+    "long_tail": lambda: case_long_tail(),
 }
 
 
