@@ -2,9 +2,21 @@ from __future__ import annotations
 
 import numpy as np
 
+import os
+
 import oracle_lib as ol
 
 from . import _objects as O
+
+
+def _engine(flat_genes):
+    """KB_REF_SHIM_ENGINE=emul: the PRODUCT's device logic compiled for the host (tests/host_emul) instead of the oracle, so that the
+    unmodified reference pipeline can run on top of this repo's own mapping code in a container without a GPU."""
+    if os.environ.get("KB_REF_SHIM_ENGINE", "oracle") == "emul":
+        import emul_lib as el
+
+        return el.EmulIndex(*flat_genes)
+    return ol.OracleDB(*flat_genes)
 
 _cache: dict = {}
 last_hits = None  # the raw oracle output of the most recent map_batch call (golden generation reads it)
@@ -31,8 +43,10 @@ class Aligner:
         O.check_supported(self.options, self.do_cigar, self.do_cs, self.do_md, self.preset)
         key = (len(queries), hash(tuple(q[1] for q in queries)))
         if key not in _cache:
-            _cache[key] = ol.OracleDB(*_flat([bytes(q[1]) for q in queries]))
-        r = _cache[key].map(*_flat(self.index.contigs))
+            _cache[key] = (os.environ.get("KB_REF_SHIM_ENGINE", "oracle"), _engine(_flat([bytes(q[1]) for q in queries])))
+        if _cache[key][0] != os.environ.get("KB_REF_SHIM_ENGINE", "oracle"):
+            _cache[key] = (os.environ.get("KB_REF_SHIM_ENGINE", "oracle"), _engine(_flat([bytes(q[1]) for q in queries])))
+        r = _cache[key][1].map(*_flat(self.index.contigs))
         last_hits = r
         per = [[] for _ in queries]
         for h in r["hits"]:
