@@ -1,16 +1,17 @@
 #!/bin/bash
-# Round-end measurement on one B200 (run under gpurun): tests, bench (both arms), ncu launch list and full captures.
-set -u
-mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4) > gpurun_out/final_gputests.log
-(timeout 900 python bench.py 2>&1 | tail -1) > gpurun_out/final_bench.json
-(timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1) > gpurun_out/final_bench_reference.json
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kb_|DeviceRadixSort|DeviceSelect|DeviceScan" --csv \
-    --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 1 --warmup 1 --e2e-asm 8 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:kb_scan_kernel -s 1 -c 1 -o gpurun_out/prof_scan_final \
-    python bench.py --steps 1 --warmup 1 --e2e-asm 8 --no-cpu-baseline > gpurun_out/ncu_scan_final.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"kb_rows_kernel|kb_band_kernel" -s 2 -c 2 -o gpurun_out/prof_dp_final \
-    python bench.py --n-asm 250 --steps 1 --warmup 1 --e2e-asm 8 --no-cpu-baseline > gpurun_out/ncu_dp_final.log 2>&1
-cat gpurun_out/final_gputests.log
-cut -c1-400 gpurun_out/final_bench.json
-cut -c1-300 gpurun_out/final_bench_reference.json
+# ncu evidence for profiles/r2_summary.md (run on the GPU box through gpurun; numbers printed under ncu are never bench values)
+set -x
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+O=gpurun_out
+# 1. launch list of one timed step of the default bench workload (K+O, 10,000 assemblies): kernel shares
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kb_|gotoh|type_translate|DeviceRadixSort|DeviceSelect|DeviceScan" --csv \
+    --log-file $O/launches_r2.csv python bench.py --steps 1 --warmup 1 --e2e-asm 512 --e2e-ascii-asm 0 --no-cpu-baseline > $O/launches_r2.log 2>&1
+# 2. the roofline kernel: one scan launch over the 10,000-assembly batch, full set (dram bytes = roofline.traffic)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:kb_scan_kernel -s 1 -c 1 -o $O/r2_scan \
+    python bench.py --steps 1 --warmup 1 --e2e-asm 512 --e2e-ascii-asm 0 --no-cpu-baseline > $O/r2_scan.log 2>&1
+ncu -i $O/r2_scan.ncu-rep --page raw --csv > $O/r2_scan_raw.csv
+# 3. the DP kernels (1000 assemblies)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"kb_rows16_kernel|kb_band_kernel|kb_rows_kernel" -s 3 -c 3 -o $O/r2_dp \
+    python bench.py --n-asm 1000 --steps 1 --warmup 1 --e2e-asm 512 --e2e-ascii-asm 0 --no-cpu-baseline > $O/r2_dp.log 2>&1
+ncu -i $O/r2_dp.ncu-rep --page raw --csv > $O/r2_dp_raw.csv
+rm -f $O/r2_scan.ncu-rep $O/r2_dp.ncu-rep

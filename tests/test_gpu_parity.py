@@ -383,6 +383,25 @@ def test_dp_over_the_fast_limit_goes_through_the_full_size_kernel(env):
     assert int(h["q_end"][h["gene"] == g][0]) == 2300  # with the extension skipped (a 4 M limit) it would stop at 2291
 
 
+def test_index_sidecar_round_trip(env, tmp_path):
+    """kaptive_b200.sidecar: the gene index cached beside the compiled database (db/manager.py:539-558 caches <kw>.pkl the same way)
+    maps exactly like a freshly built one; a stale key (other genes) is rejected and rebuilt."""
+    from kaptive_b200 import sidecar
+
+    db = env["db"]
+    pkl = tmp_path / "synth_k.pkl"
+    gi1, cached1 = sidecar.index_for(pkl, db.genes)
+    gi2, cached2 = sidecar.index_for(pkl, db.genes)
+    assert (cached1, cached2) == (False, True) and sidecar.sidecar_path(pkl).exists()
+    n = "fragmented"
+    for gi in (gi1, gi2):
+        res = gi.map_contigs([[s for _, s in env["built"][n][1]]])
+        check_against(res, 0, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
+    assert sidecar.load(sidecar.sidecar_path(pkl), db.genes[:-1]) is None
+    sidecar.sidecar_path(pkl).write_bytes(b"garbage")
+    assert sidecar.index_for(pkl, db.genes)[1] is False
+
+
 def test_one_warp_per_chain_kernel_alone_gives_the_same_hits(env, monkeypatch):
     """KAPTIVE_B200_STAGED=0 sends every chain through kb_align_kernel (all of mm_align1 in one warp), the kernel that
     otherwise only serves the chains the staged path hands back: it has to stay bit-identical."""
