@@ -316,6 +316,7 @@ KB_HD bool kb_band_eligible(int64_t max_sw_cells, int qlen, int tlen, int w, int
 #define kb_backtrack_lane0(lane, qlen, tlen, flag, ez, S) kb_backtrack<32>(lane, qlen, tlen, flag, ez, S)
 #include "kb_align_reg.cuh"
 #include "kb_align_reg16.cuh"
+#include "kb_band16.cuh"
 // device-side choice between the register-resident DP and the scratch-memory DP (identical results)
 static __device__ __noinline__ void kb_dp_device(const KbDpConst P, int lane, int qlen, const uint8_t *qs, int tlen, const uint8_t *ts,
                                                  int w, int zdrop, int flag, KbEz &ez, const KbAlignScratch S, int64_t *cell_counter)

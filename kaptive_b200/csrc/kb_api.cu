@@ -44,11 +44,10 @@ size_t kb_band_scratch_bytes();
 size_t kb_sizeof_job();
 size_t kb_sizeof_plan();
 void kb_launch_stage_plan(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
-                          uint64_t *, int32_t *, void *, void *, int64_t, int32_t *, int32_t *, int32_t *, uint32_t *, int32_t *,
-                          unsigned long long *, cudaStream_t);
+                          uint64_t *, int32_t *, void *, void *, const KbStageLists &, int32_t *, unsigned long long *, cudaStream_t);
 size_t kb_r16_sort_temp_bytes(int64_t);
-void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, int32_t *, int32_t *, int32_t *, uint32_t *, int32_t *, uint32_t *,
-                        void *, size_t, uint8_t *, int, uint8_t *, size_t, int, uint32_t *, int64_t, unsigned long long *, cudaStream_t);
+void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, const KbStageLists &, uint8_t *, int, uint8_t *, size_t, int, uint32_t *,
+                        int64_t, unsigned long long *, cudaStream_t);
 void kb_launch_stage_assemble(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const void *,
                               const void *, const uint32_t *, uint32_t *, int64_t, KbRawHit *, int64_t, uint32_t *, int64_t, int32_t *,
                               unsigned long long *, cudaStream_t);
@@ -762,18 +761,19 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         if ((int64_t)band_warps > 4 * n_chains + 4) band_warps = (int)(((4 * n_chains + 4) + 3) / 4 * 4);  // small calls: small scratch
         if (const char *e = getenv("KAPTIVE_B200_ROWS_WARPS")) rows_warps = std::min(n_warps, bt->n_sm * atoi(e));
         void *plans = nullptr, *jobs = nullptr;
-        int32_t *band_list = nullptr, *rows_list = nullptr, *r16_list = nullptr, *r16_list2 = nullptr, *slow_list = nullptr, *kscratch = nullptr;
-        uint32_t *r16_key = nullptr, *r16_key2 = nullptr;
-        uint8_t *r16_tmp = nullptr;
-        size_t r16_tmp_bytes = 0;
+        int32_t *slow_list = nullptr, *kscratch = nullptr;
+        KbStageLists L;
+        memset(&L, 0, sizeof(L));
+        L.job_cap = job_cap;
         uint32_t *jobcig = nullptr, *tmpcig = nullptr;
         uint8_t *band_scratch = nullptr;
         if (staged) {
             plans = P.get<uint8_t>((size_t)n_chains * kb_sizeof_plan());
             jobs = P.get<uint8_t>((size_t)job_cap * kb_sizeof_job());
-            band_list = P.get<int32_t>((size_t)job_cap), rows_list = P.get<int32_t>((size_t)job_cap), r16_list = P.get<int32_t>((size_t)job_cap);
-            r16_list2 = P.get<int32_t>((size_t)job_cap), r16_key = P.get<uint32_t>((size_t)job_cap), r16_key2 = P.get<uint32_t>((size_t)job_cap);
-            r16_tmp_bytes = kb_r16_sort_temp_bytes(job_cap), r16_tmp = P.get<uint8_t>(r16_tmp_bytes);
+            L.band_list = P.get<int32_t>((size_t)job_cap), L.rows_list = P.get<int32_t>((size_t)job_cap), L.r16_list = P.get<int32_t>((size_t)job_cap);
+            L.r16_list2 = P.get<int32_t>((size_t)job_cap), L.r16_key = P.get<uint32_t>((size_t)job_cap), L.r16_key2 = P.get<uint32_t>((size_t)job_cap);
+            for (int i = 0; i < 3; ++i) L.b16_list[i] = P.get<int32_t>((size_t)job_cap), L.b16_key[i] = P.get<uint32_t>((size_t)job_cap);
+            L.sort_tmp_bytes = kb_r16_sort_temp_bytes(job_cap), L.sort_tmp = P.get<uint8_t>(L.sort_tmp_bytes);
             slow_list = P.get<int32_t>((size_t)n_chains + 1), kscratch = P.get<int32_t>((size_t)n_anchors + 8);
             jobcig = P.get<uint32_t>((size_t)jobcig_cap), tmpcig = P.get<uint32_t>((size_t)jobcig_cap + (size_t)n_chains + 8);
             band_scratch = P.get<uint8_t>((size_t)band_warps * kb_band_scratch_bytes());
@@ -783,16 +783,13 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             CU(cudaMemsetAsync(d_next, 0, 8, st));
             CU(cudaMemsetAsync(d_counters + 4, 0, 16, st));
             CU(cudaMemsetAsync(d_counters + 8, 0, 8 * 8, st));
-            CU(cudaMemsetAsync(d_counters + 32, 0, 8 * 8, st));
+            CU(cudaMemsetAsync(d_counters + 32, 0, 16 * 8, st));
             if (staged) {
-                CU(cudaMemsetAsync(r16_key, 0, (size_t)job_cap * 4, st));
-                kb_launch_stage_plan(iv_fast, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, job_cap, band_list, rows_list, r16_list,
-                                     r16_key, slow_list, d_counters, st);
-                kb_launch_stage_dp(iv_fast, bv, jobs, band_list, rows_list, r16_list, r16_key, r16_list2, r16_key2, r16_tmp, r16_tmp_bytes,
-                                   band_scratch, band_warps, scratch, sbytes, rows_warps, jobcig, jobcig_cap, d_counters, st);
+                kb_launch_stage_plan(iv_fast, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, L, slow_list, d_counters, st);
+                kb_launch_stage_dp(iv_fast, bv, jobs, L, band_scratch, band_warps, scratch, sbytes, rows_warps, jobcig, jobcig_cap, d_counters, st);
                 kb_launch_stage_assemble(iv_fast, bv, chains, n_chains, ginfo, plans, jobs, jobcig, tmpcig, jobcig_cap + n_chains, raw, raw_cap, pool,
                                          pool_cap, slow_list, d_counters, st);
-                launches += 8;
+                launches += 14;
                 // chains handed back (a DP problem over the fast limit, a z-drop inside a gap fill, a capacity limit): full-size kernel
                 unsigned long long n_slow = 0;
                 CU(cudaMemcpyAsync(&n_slow, d_counters + 12, 8, cudaMemcpyDeviceToHost, st));
@@ -825,8 +822,9 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         P.release(scratch);
         if (slow_scratch) CU(cudaFreeAsync(slow_scratch, st));
         if (staged) {
-            P.release(plans), P.release(jobs), P.release(band_list), P.release(rows_list), P.release(r16_list), P.release(slow_list), P.release(kscratch);
-            P.release(r16_list2), P.release(r16_key), P.release(r16_key2), P.release(r16_tmp);
+            P.release(plans), P.release(jobs), P.release(L.band_list), P.release(L.rows_list), P.release(L.r16_list), P.release(slow_list), P.release(kscratch);
+            P.release(L.r16_list2), P.release(L.r16_key), P.release(L.r16_key2), P.release(L.sort_tmp);
+            for (int i = 0; i < 3; ++i) P.release(L.b16_list[i]), P.release(L.b16_key[i]);
             P.release(jobcig), P.release(tmpcig), P.release(band_scratch);
         }
         CU(cudaEventRecord(ev[4], st));

@@ -268,6 +268,20 @@ void kb_launch_align(const KbIndexView &ix, const KbBatchView &bt, const KbChain
 #define KB_SC_R16 35
 #define KB_SC_R16_BIG 36
 #define KB_SC_QR16 37
+// the packed 16-bit band pass (kb_band16): one queue per window width K = 1, 2, 4 (+0..2: jobs queued, +3..5: queue cursors), each sorted
+// by length before its kernel runs; what a pass rejects goes to the next wider queue or to the rows queues
+#define KB_SC_B16 40
+struct KbBandQueues {
+    int32_t *list[3];
+    uint32_t *key[3];   // qlen + tlen of every queued job (> 0; unused slots hold 0)
+    int32_t *band32;    // the 32-bit band kernel's list: fills outside kb_band16's range, pairs with an ambiguous target base
+    int use16;
+};
+__device__ __forceinline__ void kb_band16_enqueue(const KbBandQueues &BQ, unsigned long long *counters, int stage, const KbJob &J, int32_t jid)
+{
+    const unsigned long long k = atomicAdd(&counters[KB_SC_B16 + stage], 1ull);
+    BQ.list[stage][k] = jid, BQ.key[stage][k] = (uint32_t)(J.qlen + J.tlen);
+}
 struct KbRowsQueues {
     int32_t *rows_list, *r16_list;
     uint32_t *r16_key;  // size class of every job in r16_list: the list is sorted by it (descending) and neighbours are paired
@@ -286,7 +300,7 @@ __device__ __forceinline__ void kb_rows_enqueue(const KbRowsQueues &Q, const KbD
 }
 __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchView bt, const KbChainRec *chains, int64_t n_chains,
                                                       const KbGroupInfo *ginfo, const uint64_t *cx, uint64_t *cy, int32_t *kscratch,
-                                                      KbPlan *plans, KbJob *jobs, int64_t job_cap, int32_t *band_list, KbRowsQueues Q,
+                                                      KbPlan *plans, KbJob *jobs, int64_t job_cap, KbBandQueues BQ, KbRowsQueues Q,
                                                       int32_t *slow_list, unsigned long long *counters)
 {
     const int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,7 +332,8 @@ __global__ void __launch_bounds__(128) kb_plan_kernel(KbIndexView ix, KbBatchVie
     for (int k = 0; k < nj; ++k) {
         const KbJob &J = jobs[base + k];
         const bool band = J.kind == KB_JOB_FILL && J.qlen + J.tlen <= 8184 && kb_band_eligible(ix.p.max_sw_cells, J.qlen, J.tlen, J.w, J.flag);
-        if (band) band_list[atomicAdd(&counters[KB_SC_BAND], 1ull)] = (int32_t)(base + k);
+        if (band && BQ.use16 && kb_band16_eligible(P, J.qlen, J.tlen)) kb_band16_enqueue(BQ, counters, 0, J, (int32_t)(base + k));
+        else if (band) BQ.band32[atomicAdd(&counters[KB_SC_BAND], 1ull)] = (int32_t)(base + k);
         else kb_rows_enqueue(Q, P, counters, J, (int32_t)(base + k));
     }
 }
@@ -391,6 +406,83 @@ __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView 
         }
         if (ok) kb_job_finish(lane, J, ez, S.ezcig, jobcig, jobcig_cap, counters);
         else if (lane == 0) kb_rows_enqueue(Q, P, counters, *J, jid);
+    }
+    if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
+}
+
+
+// packed certified band pass over the gap fills: one warp per PAIR of jobs (neighbours of the length-sorted queue), persistent
+#ifndef KB_BAND16_MINB
+#define KB_BAND16_MINB 5
+#endif
+template <int K>
+__global__ void __launch_bounds__(128, KB_BAND16_MINB) kb_band16_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *sorted, KbBandQueues BQ,
+                                                                         KbRowsQueues Q, uint8_t *scratch, size_t scratch_bytes, uint32_t *jobcig,
+                                                                         int64_t jobcig_cap, unsigned long long *counters)
+{
+    constexpr int STAGE = K == 1 ? 0 : (K == 2 ? 1 : 2);
+    __shared__ __align__(8) uint8_t sm_stage[4][KB_B16_SMEM_BYTES];
+    __shared__ uint2 sm_lut[25];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + wi;
+    const KbDpConst P = kb_dp_const(ix.p);
+    if (threadIdx.x < 25) sm_lut[threadIdx.x] = make_uint2(kb_qrow16(P, 7, threadIdx.x % 5), kb_qrow16(P, 7, threadIdx.x / 5));
+    __syncthreads();
+    uint32_t *ezcig = reinterpret_cast<uint32_t *>(scratch + (size_t)wg * scratch_bytes);
+    uint32_t *tbA = ezcig + KB_CIG_MAX, *tbB = tbA + ((scratch_bytes - (size_t)KB_CIG_MAX * 4) / 8);
+    uint16_t *st_sel = reinterpret_cast<uint16_t *>(sm_stage[wi]);
+    uint8_t *st_q = sm_stage[wi] + 2 * KB_B16_X;
+    const unsigned a_sel = (unsigned)__cvta_generic_to_shared(st_sel), a_q = (unsigned)__cvta_generic_to_shared(st_q),
+                   a_lut = (unsigned)__cvta_generic_to_shared(sm_lut);
+    const long long n = (long long)counters[KB_SC_B16 + STAGE], n_pairs = (n + 1) >> 1;
+    int64_t cells = 0;
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(&counters[KB_SC_B16 + 3 + STAGE], 1ull);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if ((long long)k >= n_pairs) break;
+        const int jid[2] = {sorted[2 * k], (long long)(2 * k + 1) < n ? sorted[2 * k + 1] : -1};
+        KbJob *J[2] = {jobs + jid[0], jid[1] >= 0 ? jobs + jid[1] : jobs + jid[0]};
+        const bool haveB = jid[1] >= 0;
+        KbB16Job V[2];
+        for (int w = 0; w < 2; ++w) V[w] = kb_b16_job(P, K, J[w]->qlen, J[w]->tlen);
+        const KbDirBytes qsA{(J[0]->qrev ? ix.gseq_rev : ix.gseq_fwd) + J[0]->qbase + J[0]->qoff, 1},
+            qsB{(J[1]->qrev ? ix.gseq_rev : ix.gseq_fwd) + J[1]->qbase + J[1]->qoff, 1};
+        const KbDirPack tsA{bt.seq2, bt.nmask, J[0]->tpos, 1}, tsB{bt.seq2, bt.nmask, J[1]->tpos, 1};
+        __syncwarp();
+        if (kb_band16_stage(lane, K, V[0], qsA, tsA, V[1], qsB, tsB, st_sel, st_q)) {  // an ambiguous target base: the 32-bit kernel takes both
+            if (lane == 0)
+                for (int w = 0; w < (haveB ? 2 : 1); ++w) BQ.band32[atomicAdd(&counters[KB_SC_BAND], 1ull)] = jid[w];
+            continue;
+        }
+        KbB16Out out;
+        kb_band16_pass<K>(P, lane, V[0], V[1], haveB, a_sel, a_q, a_lut, tbA, tbB, out);
+        __syncwarp();
+        for (int w = 0; w < (haveB ? 2 : 1); ++w) {
+            const int score = out.score[w];
+            int ok = out.state[w] == 1 && score > V[w].bound, n_cigar = 0;
+            if (ok) {
+                n_cigar = kb_band16_backtrack<K>(lane, V[w], J[w]->flag, w ? tbB : tbA, ezcig);
+                if (n_cigar < 0) ok = 0;
+            }
+            cells += (int64_t)32 * K * out.steps[w];
+            if (lane == 0) KB_DP_STAT(K == 1 ? 0 : 2, ok ? 0 : 1, (int64_t)32 * K * (V[w].r_end + 1));
+            if (ok) {
+                KbEz ez;
+                ez.max = 0, ez.max_q = ez.max_t = -1, ez.zdropped = 0, ez.score = score, ez.n_cigar = n_cigar;
+                kb_job_finish(lane, J[w], ez, ezcig, jobcig, jobcig_cap, counters);
+                continue;
+            }
+            if (lane == 0) {  // the smallest wider window this score (a lower bound of every wider pass's score) already certifies, if any
+                const int ql = V[w].qlen, tl = V[w].tlen;
+                int k2 = 0, dlo, dhi;
+                if (K == 1 && kb_band16_geometry(ql, tl, 2, dlo, dhi) && score > kb_band_bound64(P, ql, tl, dlo, dhi)) k2 = 2;
+                else if (K <= 2 && kb_band16_geometry(ql, tl, 4, dlo, dhi) && score > kb_band_bound64(P, ql, tl, dlo, dhi)) k2 = 4;
+                // worth it only while the window stays well below the rectangle
+                if (k2 && 64 * k2 * 3 <= 2 * (ql + tl)) kb_band16_enqueue(BQ, counters, k2 == 2 ? 1 : 2, *J[w], jid[w]);
+                else kb_rows_enqueue(Q, P, counters, *J[w], jid[w]);
+            }
+        }
     }
     if (lane == 0 && cells) atomicAdd(&counters[8], (unsigned long long)cells);
 }
@@ -552,15 +644,29 @@ static int kb_use_rows16()
     static const int v = !(getenv("KAPTIVE_B200_ROWS16") && getenv("KAPTIVE_B200_ROWS16")[0] == '0');
     return v;
 }
+static int kb_use_band16()
+{
+    static const int v = !(getenv("KAPTIVE_B200_BAND16") && getenv("KAPTIVE_B200_BAND16")[0] == '0');
+    return v;
+}
+static KbBandQueues kb_band_queues(const KbStageLists &L)
+{
+    KbBandQueues BQ;
+    for (int i = 0; i < 3; ++i) BQ.list[i] = L.b16_list[i], BQ.key[i] = L.b16_key[i];
+    BQ.band32 = L.band_list, BQ.use16 = kb_use_band16();
+    return BQ;
+}
 void kb_launch_stage_plan(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
-                          const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, int64_t job_cap, int32_t *band_list,
-                          int32_t *rows_list, int32_t *r16_list, uint32_t *r16_key, int32_t *slow_list, unsigned long long *counters,
-                          cudaStream_t st)
+                          const uint64_t *cx, uint64_t *cy, int32_t *kscratch, void *plans, void *jobs, const KbStageLists &L, int32_t *slow_list,
+                          unsigned long long *counters, cudaStream_t st)
 {
     if (n_chains <= 0) return;
-    const KbRowsQueues Q{rows_list, r16_list, r16_key, job_cap, kb_rows_big_thr(), kb_use_rows16()};
+    // unused slots of the sorted queues must hold key 0
+    cudaMemsetAsync(L.r16_key, 0, (size_t)L.job_cap * 4, st);
+    for (int i = 0; i < 3; ++i) cudaMemsetAsync(L.b16_key[i], 0, (size_t)L.job_cap * 4, st);
+    const KbRowsQueues Q{L.rows_list, L.r16_list, L.r16_key, L.job_cap, kb_rows_big_thr(), kb_use_rows16()};
     kb_plan_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(ix, bt, chains, n_chains, ginfo, cx, cy, kscratch, (KbPlan *)plans,
-                                                                       (KbJob *)jobs, job_cap, band_list, Q, slow_list, counters);
+                                                                       (KbJob *)jobs, L.job_cap, kb_band_queues(L), Q, slow_list, counters);
 }
 size_t kb_r16_sort_temp_bytes(int64_t n)
 {
@@ -569,23 +675,32 @@ size_t kb_r16_sort_temp_bytes(int64_t n)
                                               (int32_t *)nullptr, n, 0, 29);
     return b;
 }
-// r16_key / r16_list: job_cap entries (unused ones hold key 0); r16_key2 / r16_list2: the sorted copies; sort_tmp: kb_r16_sort_temp_bytes
-void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, int32_t *band_list, int32_t *rows_list, int32_t *r16_list,
-                        uint32_t *r16_key, int32_t *r16_list2, uint32_t *r16_key2, void *sort_tmp, size_t sort_tmp_bytes, uint8_t *band_scratch,
-                        int band_warps, uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
+// every queue that is sorted: job_cap entries (unused ones hold key 0), sorted copies in r16_key2 / r16_list2
+void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, const KbStageLists &L, uint8_t *band_scratch, int band_warps,
+                        uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
                         unsigned long long *counters, cudaStream_t st)
 {
-    const int64_t job_cap = jobcig_cap / 16;
-    const KbRowsQueues Q{rows_list, r16_list, r16_key, job_cap, kb_rows_big_thr(), kb_use_rows16()};
-    kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, band_list, Q, band_scratch, kb_band_scratch_bytes(), jobcig,
+    const KbRowsQueues Q{L.rows_list, L.r16_list, L.r16_key, L.job_cap, kb_rows_big_thr(), kb_use_rows16()};
+    const KbBandQueues BQ = kb_band_queues(L);
+    size_t tmp = L.sort_tmp_bytes;
+    if (BQ.use16) {  // K = 1, then what it handed on at K = 2, then K = 4: each queue sorted by length, neighbours share a warp
+        const unsigned g = (unsigned)(band_warps / 4);
+        cub::DeviceRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.b16_key[0], L.r16_key2, L.b16_list[0], L.r16_list2, L.job_cap, 0, 13, st);
+        kb_band16_kernel<1><<<g, 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.r16_list2, BQ, Q, band_scratch, kb_band_scratch_bytes(), jobcig, jobcig_cap, counters);
+        cub::DeviceRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.b16_key[1], L.r16_key2, L.b16_list[1], L.r16_list2, L.job_cap, 0, 13, st);
+        kb_band16_kernel<2><<<g, 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.r16_list2, BQ, Q, band_scratch, kb_band_scratch_bytes(), jobcig, jobcig_cap, counters);
+        cub::DeviceRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.b16_key[2], L.r16_key2, L.b16_list[2], L.r16_list2, L.job_cap, 0, 13, st);
+        kb_band16_kernel<4><<<g, 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.r16_list2, BQ, Q, band_scratch, kb_band_scratch_bytes(), jobcig, jobcig_cap, counters);
+    }
+    kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.band_list, Q, band_scratch, kb_band_scratch_bytes(), jobcig,
                                                                jobcig_cap, counters);
     int r16_warps = rows_warps / 4 * 4;
     if (kb_use_rows16()) {
-        cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sort_tmp_bytes, r16_key, r16_key2, r16_list, r16_list2, job_cap, 0, 29, st);
-        kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, r16_list2, rows_scratch, rows_scratch_bytes, jobcig,
+        cub::DeviceRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.r16_key, L.r16_key2, L.r16_list, L.r16_list2, L.job_cap, 0, 29, st);
+        kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.r16_list2, rows_scratch, rows_scratch_bytes, jobcig,
                                                                     jobcig_cap, counters);
     }
-    kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, rows_list, rows_scratch, rows_scratch_bytes, jobcig,
+    kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.rows_list, rows_scratch, rows_scratch_bytes, jobcig,
                                                                jobcig_cap, counters);
 }
 void kb_launch_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
@@ -687,15 +802,22 @@ extern "C" int kb_debug_dp_stats(int64_t *out32, int reset)
 
 // ------------------------------------------------------------------ DP kernels one by one (diagnostic / parity tests)
 // One warp per job; mode 0 = scratch-memory DP (kb_extd2, the statement closest to the oracle), 1 = kb_rows, 2 = kb_rows16,
-// 3 = certified band pass (kb_global_band).  out: n x 8 = score, max, max_t, max_q, zdropped, n_cigar, ran (0: not eligible), 0.
+// 3 = certified band pass (kb_global_band), 4 = kb_rows16 paired, 5 / 6 / 7 = packed band pass (kb_band16) with K = 1 / 2 / 4, paired.
+// out: n x 8 = score, max, max_t, max_q, zdropped, n_cigar, ran (0: not eligible, 2: ran, not certified), pass state (kb_band16).
 __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const uint8_t *q, const int64_t *qoff, const int32_t *qlen,
                                                           const uint8_t *t, const int64_t *toff, const int32_t *tlen, const int32_t *flag,
                                                           const int32_t *w, const int32_t *zdrop, int n, int mode, uint8_t *scratch,
                                                           size_t scratch_bytes, int32_t *out, uint32_t *cig, int cig_stride)
 {
     __shared__ uint32_t wmax_ring[4][KB_R16_SMEM_WORDS];
+    __shared__ uint2 dbg_lut[25];
     const int lane = threadIdx.x & 31;
     const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    {
+        const KbDpConst P0 = kb_dp_const(pp);
+        if (threadIdx.x < 25) dbg_lut[threadIdx.x] = make_uint2(kb_qrow16(P0, 7, threadIdx.x % 5), kb_qrow16(P0, 7, threadIdx.x / 5));
+        __syncthreads();
+    }
     KbAlignScratch S = kb_align_scratch_at(scratch + (size_t)wg * scratch_bytes, pp.max_sw_cells);
     S.wmax = wmax_ring[threadIdx.x >> 5];
     for (int x = lane; x < KB_R16_SMEM_WORDS; x += 32) S.wmax[x] = 0;
@@ -707,7 +829,7 @@ __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const 
         const bool track = !(fl & KB_EZ_GLOBAL_NO_ZDROP);
         KbEz ez;
         ez.max = 0, ez.max_q = ez.max_t = -1, ez.score = KB_NEG_INF, ez.zdropped = 0, ez.n_cigar = 0;
-        int ran = 1;
+        int ran = 1, o7 = 0;
         if (mode == 0) kb_extd2<32>(P, lane, ql, sq.p, tl, st.p, ww, zd, fl, ez, S, nullptr);
         else if (mode == 1) {
             if (!kb_rows_eligible(P.max_sw_cells, ql, tl, ww, track)) ran = 0;
@@ -734,6 +856,50 @@ __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const 
                 if (tr) kb_rows16_dp<true>(P, lane, A, B, po, S), kb_rows16_finish<true>(P, lane, me, me_hi ? 1 : 0, other.tlen, po, ez, S, nullptr);
                 else kb_rows16_dp<false>(P, lane, A, B, po, S), kb_rows16_finish<false>(P, lane, me, me_hi ? 1 : 0, other.tlen, po, ez, S, nullptr);
             }
+        } else if (mode >= 5) {
+            // modes 5, 6, 7: the packed band pass with K = 1, 2, 4, paired with job k ^ 1 (this job in the low half when k is even)
+            const int K = mode == 5 ? 1 : (mode == 6 ? 2 : 4);
+            const int64_t ko = (k ^ 1) < n ? (k ^ 1) : -1;
+            int dlo, dhi;
+            auto fits = [&](int64_t x) {
+                return kb_band_eligible(P.max_sw_cells, qlen[x], tlen[x], w[x], flag[x]) && kb_band16_eligible(P, qlen[x], tlen[x]) &&
+                       kb_band16_geometry(qlen[x], tlen[x], K, dlo, dhi);
+            };
+            if (!fits(k)) ran = 0;
+            else {
+                const bool pair = ko >= 0 && fits(ko), me_hi = pair && (k & 1);
+                const int64_t ka = me_hi ? ko : k, kb = pair ? (me_hi ? k : ko) : k;
+                const KbB16Job A = kb_b16_job(P, K, qlen[ka], tlen[ka]), B = kb_b16_job(P, K, qlen[kb], tlen[kb]);
+                uint16_t *st_sel = reinterpret_cast<uint16_t *>(S.wmax);
+                uint8_t *st_q = reinterpret_cast<uint8_t *>(S.wmax) + 2 * KB_B16_X;
+                uint32_t *tbA = reinterpret_cast<uint32_t *>(S.tb), *tbB = tbA + (P.max_sw_cells >> 3);
+                const bool amb = kb_band16_stage(lane, K, A, KbPtrSeq{q + qoff[ka]}, KbPtrSeq{t + toff[ka]}, B, KbPtrSeq{q + qoff[kb]},
+                                                 KbPtrSeq{t + toff[kb]}, st_sel, st_q);
+                if (amb) ran = 0;
+                else {
+                    KbB16Out po;
+                    const unsigned a_sel = (unsigned)__cvta_generic_to_shared(st_sel), a_q = (unsigned)__cvta_generic_to_shared(st_q),
+                                   a_lut = (unsigned)__cvta_generic_to_shared(dbg_lut);
+                    if (K == 1) kb_band16_pass<1>(P, lane, A, B, pair, a_sel, a_q, a_lut, tbA, tbB, po);
+                    else if (K == 2) kb_band16_pass<2>(P, lane, A, B, pair, a_sel, a_q, a_lut, tbA, tbB, po);
+                    else kb_band16_pass<4>(P, lane, A, B, pair, a_sel, a_q, a_lut, tbA, tbB, po);
+                    __syncwarp();
+                    const int wme = me_hi ? 1 : 0;
+                    const KbB16Job &M = me_hi ? B : A;
+                    ez.score = po.score[wme], ran = 2;
+                    if (po.state[wme] == 1 && po.score[wme] > M.bound) {
+                        const uint32_t *tbm = me_hi ? tbB : tbA;
+                        const int nc = K == 1 ? kb_band16_backtrack<1>(lane, M, fl, tbm, S.ezcig)
+                                              : (K == 2 ? kb_band16_backtrack<2>(lane, M, fl, tbm, S.ezcig) : kb_band16_backtrack<4>(lane, M, fl, tbm, S.ezcig));
+                        if (nc >= 0) ez.n_cigar = nc, ran = 1;
+                    }
+                    o7 = po.state[wme];
+                }
+                // the staging area doubles as kb_rows16's rings: leave it zeroed
+                __syncwarp();
+                for (int x = lane; x < KB_R16_SMEM_WORDS; x += 32) S.wmax[x] = 0;
+                __syncwarp();
+            }
         } else {
             if (!kb_band_eligible(P.max_sw_cells, ql, tl, ww, fl)) ran = 0;
             else ran = kb_global_band(P, lane, ql, sq, tl, st, fl, ez, S, nullptr) ? 1 : 2;  // 2: ran, not certified
@@ -741,7 +907,7 @@ __global__ void __launch_bounds__(128) kb_debug_dp_kernel(kb_params_t pp, const 
         __syncwarp();
         if (lane == 0) {
             int32_t *o = out + k * 8;
-            o[0] = ez.score, o[1] = ez.max, o[2] = ez.max_t, o[3] = ez.max_q, o[4] = ez.zdropped, o[5] = ez.n_cigar, o[6] = ran, o[7] = 0;
+            o[0] = ez.score, o[1] = ez.max, o[2] = ez.max_t, o[3] = ez.max_q, o[4] = ez.zdropped, o[5] = ez.n_cigar, o[6] = ran, o[7] = o7;
         }
         if (ran == 1)
             for (int i = lane; i < ez.n_cigar && i < cig_stride; i += 32) cig[k * (int64_t)cig_stride + i] = S.ezcig[i];

@@ -121,3 +121,59 @@ def test_rows16_range_limits_fall_back():
     fl, w, zd = np.array([EXTZ_ONLY, EXTZ_ONLY], np.int32), np.array([751, 751], np.int32), np.array([400, 400], np.int32)
     got, _ = run(L, P, q, t, fl, w, zd, 2)
     assert got[:, 6].tolist() == [0, 1]
+
+
+def make_fills(seed: int, n: int):
+    """Global gap fills of every size the packed band pass takes (qlen + tlen <= 3000), neighbours unrelated in size and divergence."""
+    rng = np.random.default_rng(seed)
+    q, t = [], []
+    for i in range(n):
+        ql = int(rng.choice([rng.integers(33, 80), rng.integers(60, 300), rng.integers(250, 900), rng.integers(800, 1480)]))
+        qs = rng.integers(0, 4, size=ql).astype(np.uint8)
+        sub = float(rng.choice([0.0, 0.01, 0.04, 0.1, 0.18, 0.3]))
+        ind = float(rng.choice([0.0, 0.004, 0.02]))
+        ts = _mutate(rng, qs, sub, ind)
+        if rng.random() < 0.35 and len(ts) > 80:  # one long indel: what the wider windows are for
+            c = int(rng.integers(20, len(ts) - 20))
+            g = int(rng.integers(5, 110))
+            ts = np.concatenate([ts[:c], rng.integers(0, 4, size=g).astype(np.uint8), ts[c:]]) if rng.random() < 0.5 else np.concatenate([ts[:c], ts[c + g:]])
+        ts = ts[:1490]
+        if len(ts) < 33:
+            ts = np.concatenate([ts, rng.integers(0, 4, size=40).astype(np.uint8)])
+        if rng.random() < 0.15:
+            qs[rng.integers(0, len(qs), size=2)] = 4  # ambiguous query bases stay in the packed pass
+        if rng.random() < 0.05:
+            ts[rng.integers(0, len(ts))] = 4          # an ambiguous target base sends the pair to the 32-bit kernel
+        q.append(qs), t.append(ts.astype(np.uint8))
+    fl = np.full(n, GLOBAL, np.int32)
+    return q, t, fl, np.full(n, 30001, np.int32), np.full(n, -1, np.int32)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_packed_band_pass_equals_the_scratch_dp(seed):
+    """kb_band16 (two fills per warp, window of 64 / 128 / 256 diagonals): whatever it certifies is the full DP's alignment, bit for bit."""
+    from kaptive_b200 import _lib
+
+    L = _lib.load()
+    P = _lib.default_params()
+    q, t, fl, w, zd = make_fills(seed, 800)
+    ref, rcig = run(L, P, q, t, fl, w, zd, 0)
+    legacy, _ = run(L, P, q, t, fl, w, zd, 3)
+    n_ok = {}
+    for mode, K in ((5, 1), (6, 2), (7, 4)):
+        got, gcig = run(L, P, q, t, fl, w, zd, mode)
+        ok = got[:, 6] == 1
+        n_ok[K] = int(ok.sum())
+        for i in np.nonzero(ok)[0]:
+            desc = (K, int(i), len(q[i]), len(t[i]))
+            assert got[i, 0] == ref[i, 0], (desc, "score", got[i].tolist(), ref[i].tolist())
+            assert got[i, 5] == ref[i, 5], (desc, "n_cigar", got[i].tolist(), ref[i].tolist())
+            nc = int(ref[i, 5])
+            assert np.array_equal(gcig[i, :nc], rcig[i, :nc]), (desc, "cigar")
+        # a pass that ran to the end without certifying still holds a valid alignment's score: a lower bound of the optimum
+        low = (got[:, 6] == 2) & (got[:, 7] == 1)
+        assert np.all(got[low, 0] <= ref[low, 0]), K
+        if K == 1:  # the 64-diagonal window certifies (nearly) what the 32-bit pass certifies: its band may sit one diagonal lower
+            both = (legacy[:, 6] == 1) & (got[:, 6] != 0)
+            assert (got[both, 6] == 1).mean() > 0.97
+    assert n_ok[1] > 150 and n_ok[2] > n_ok[1] and n_ok[4] > n_ok[2], n_ok
