@@ -46,8 +46,8 @@ size_t kb_sizeof_plan();
 void kb_launch_stage_plan(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
                           uint64_t *, int32_t *, void *, void *, const KbStageLists &, int32_t *, unsigned long long *, cudaStream_t);
 size_t kb_r16_sort_temp_bytes(int64_t);
-void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, const KbStageLists &, uint8_t *, int, uint8_t *, size_t, int, uint32_t *,
-                        int64_t, unsigned long long *, cudaStream_t);
+void kb_launch_stage_dp(const KbIndexView &, const KbBatchView &, void *, const KbStageLists &, uint8_t *, int, uint8_t *, size_t, int, uint8_t *,
+                        int, uint32_t *, int64_t, unsigned long long *, cudaStream_t);
 void kb_launch_stage_assemble(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const void *,
                               const void *, const uint32_t *, uint32_t *, int64_t, KbRawHit *, int64_t, uint32_t *, int64_t, int32_t *,
                               unsigned long long *, cudaStream_t);
@@ -766,7 +766,8 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
         memset(&L, 0, sizeof(L));
         L.job_cap = job_cap;
         uint32_t *jobcig = nullptr, *tmpcig = nullptr;
-        uint8_t *band_scratch = nullptr;
+        uint8_t *band_scratch = nullptr, *side_scratch = nullptr;
+        int side_warps = 0;
         if (staged) {
             plans = P.get<uint8_t>((size_t)n_chains * kb_sizeof_plan());
             jobs = P.get<uint8_t>((size_t)job_cap * kb_sizeof_job());
@@ -777,6 +778,9 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             slow_list = P.get<int32_t>((size_t)n_chains + 1), kscratch = P.get<int32_t>((size_t)n_anchors + 8);
             jobcig = P.get<uint32_t>((size_t)jobcig_cap), tmpcig = P.get<uint32_t>((size_t)jobcig_cap + (size_t)n_chains + 8);
             band_scratch = P.get<uint8_t>((size_t)band_warps * kb_band_scratch_bytes());
+            // the 32-bit rows kernel next to the packed one (kb_launch_stage_dp): its own scratch, one CTA per SM is plenty for what is left to it
+            side_warps = std::min(rows_warps, bt->n_sm * 4) / 4 * 4;
+            if (side_warps >= 4 && rows_warps >= bt->n_sm * 4) side_scratch = P.get<uint8_t>((size_t)side_warps * sbytes);
         }
         for (int attempt = 0;; ++attempt) {
             CU(cudaMallocAsync((void **)&pool, (size_t)pool_cap * 4 + 16, st));
@@ -786,7 +790,8 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             CU(cudaMemsetAsync(d_counters + 32, 0, 16 * 8, st));
             if (staged) {
                 kb_launch_stage_plan(iv_fast, bv, chains, n_chains, ginfo, cx, cy, kscratch, plans, jobs, L, slow_list, d_counters, st);
-                kb_launch_stage_dp(iv_fast, bv, jobs, L, band_scratch, band_warps, scratch, sbytes, rows_warps, jobcig, jobcig_cap, d_counters, st);
+                kb_launch_stage_dp(iv_fast, bv, jobs, L, band_scratch, band_warps, scratch, sbytes, rows_warps, side_scratch, side_warps, jobcig,
+                                   jobcig_cap, d_counters, st);
                 kb_launch_stage_assemble(iv_fast, bv, chains, n_chains, ginfo, plans, jobs, jobcig, tmpcig, jobcig_cap + n_chains, raw, raw_cap, pool,
                                          pool_cap, slow_list, d_counters, st);
                 launches += 14;
@@ -826,6 +831,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             P.release(L.r16_list2), P.release(L.r16_key), P.release(L.r16_key2), P.release(L.sort_tmp);
             for (int i = 0; i < 3; ++i) P.release(L.b16_list[i]), P.release(L.b16_key[i]);
             P.release(jobcig), P.release(tmpcig), P.release(band_scratch);
+            if (side_scratch) P.release(side_scratch);
         }
         CU(cudaEventRecord(ev[4], st));
         R->counters[4] = n_raw, R->counters[6] = (int64_t)hc[8];

@@ -677,8 +677,8 @@ size_t kb_r16_sort_temp_bytes(int64_t n)
 }
 // every queue that is sorted: job_cap entries (unused ones hold key 0), sorted copies in r16_key2 / r16_list2
 void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs, const KbStageLists &L, uint8_t *band_scratch, int band_warps,
-                        uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint32_t *jobcig, int64_t jobcig_cap,
-                        unsigned long long *counters, cudaStream_t st)
+                        uint8_t *rows_scratch, size_t rows_scratch_bytes, int rows_warps, uint8_t *side_scratch, int side_warps, uint32_t *jobcig,
+                        int64_t jobcig_cap, unsigned long long *counters, cudaStream_t st)
 {
     const KbRowsQueues Q{L.rows_list, L.r16_list, L.r16_key, L.job_cap, kb_rows_big_thr(), kb_use_rows16()};
     const KbBandQueues BQ = kb_band_queues(L);
@@ -694,14 +694,42 @@ void kb_launch_stage_dp(const KbIndexView &ix, const KbBatchView &bt, void *jobs
     }
     kb_band_kernel<<<(unsigned)(band_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.band_list, Q, band_scratch, kb_band_scratch_bytes(), jobcig,
                                                                jobcig_cap, counters);
+    // The 32-bit rows kernel is left with the few rectangles outside the packed kernel's range: long single-warp jobs (14 ms for ~20 jobs
+    // per 1000 assemblies).  It runs on a side stream next to the packed kernel, in its own scratch (side_scratch, one slot per warp of
+    // side_warps), instead of after it.
     int r16_warps = rows_warps / 4 * 4;
+    cudaStream_t s2 = st;
+    cudaEvent_t e_fork = nullptr, e_join = nullptr;
+    if (kb_use_rows16() && side_scratch) {
+        static thread_local struct Side {
+            int dev = -1;
+            cudaStream_t s = nullptr;
+            cudaEvent_t a = nullptr, b = nullptr;
+        } side;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (side.dev != dev) {
+            if (side.s) cudaStreamDestroy(side.s), cudaEventDestroy(side.a), cudaEventDestroy(side.b);
+            cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&side.a, cudaEventDisableTiming), cudaEventCreateWithFlags(&side.b, cudaEventDisableTiming);
+            side.dev = dev;
+        }
+        s2 = side.s, e_fork = side.a, e_join = side.b;
+        cudaEventRecord(e_fork, st);
+        cudaStreamWaitEvent(s2, e_fork, 0);
+        kb_rows_kernel<<<(unsigned)(side_warps / 4), 128, 0, s2>>>(ix, bt, (KbJob *)jobs, L.rows_list, side_scratch, rows_scratch_bytes, jobcig, jobcig_cap,
+                                                                  counters);
+        cudaEventRecord(e_join, s2);
+    }
     if (kb_use_rows16()) {
         cub::DeviceRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.r16_key, L.r16_key2, L.r16_list, L.r16_list2, L.job_cap, 0, 29, st);
         kb_rows16_kernel<<<(unsigned)(r16_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.r16_list2, rows_scratch, rows_scratch_bytes, jobcig,
                                                                     jobcig_cap, counters);
     }
-    kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.rows_list, rows_scratch, rows_scratch_bytes, jobcig,
-                                                               jobcig_cap, counters);
+    if (s2 != st) cudaStreamWaitEvent(st, e_join, 0);
+    else
+        kb_rows_kernel<<<(unsigned)(rows_warps / 4), 128, 0, st>>>(ix, bt, (KbJob *)jobs, L.rows_list, rows_scratch, rows_scratch_bytes, jobcig, jobcig_cap,
+                                                                   counters);
 }
 void kb_launch_stage_assemble(const KbIndexView &ix, const KbBatchView &bt, const KbChainRec *chains, int64_t n_chains, const KbGroupInfo *ginfo,
                               const void *plans, const void *jobs, const uint32_t *jobcig, uint32_t *tmpcig, int64_t tmpcig_cap, KbRawHit *raw,
