@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--e2e-ascii-asm", type=int, default=1000, help="assemblies per end-to-end step of the ASCII variant (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="assemblies in the CPU baseline sample (0 = 4 x cores, 64..96)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="copies of an insertion-sequence-like element (the first extra gene of the db) written into every assembly: with more "
+                         "than 10 copies every assembly takes the occurrence-census path (mm_idx_cal_max_occ); 0 = the headline workload")
     a = ap.parse_args()
     global METRIC
     if a.db == "k":
@@ -65,12 +68,13 @@ def parse_args():
 
 
 def workload_name(a) -> str:
+    rep = f"; + {a.repeats} copies of an insertion-sequence-like db gene per assembly (every assembly takes the occurrence census)" if a.repeats > 0 else ""
     if a.db == "ko":
         return (f"BASELINE configs[2]: {a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU (one resident packed batch), a K and an O "
                 f"locus embedded in each, vs kpsc_k + kpsc_o shaped db in ONE index (K {a.n_loci} loci x {a.genes_per_locus} genes, "
-                f"{a.n_core} core families; O 20 loci x 10 genes, 2 core families, + 15 extra genes)")
+                f"{a.n_core} core families; O 20 loci x 10 genes, 2 core families, + 15 extra genes)" + rep)
     return (f"BASELINE configs[1]: {a.n_asm} synthetic {a.asm_len / 1e6:g} Mb assemblies/GPU vs kpsc_k-shaped db "
-            f"({a.n_loci} loci x {a.genes_per_locus} genes, {a.n_core} core families)")
+            f"({a.n_loci} loci x {a.genes_per_locus} genes, {a.n_core} core families)" + rep)
 
 
 def make_db(a):
@@ -80,6 +84,16 @@ def make_db(a):
     if a.db == "ko":
         return synth.make_ko_db(k_loci=a.n_loci, k_genes=a.genes_per_locus, k_core=a.n_core, seed=1)
     return synth.make_db(n_loci=a.n_loci, genes_per_locus=a.genes_per_locus, n_core=a.n_core, seed=1), None
+
+
+def repeat_args(a, db):
+    """--repeats: the element is the first extra gene of the database (not part of any locus), or gene 0 when there is none"""
+    if a.repeats <= 0:
+        return {}
+    import numpy as np
+
+    ex = np.nonzero(db.extra)[0]
+    return {"repeats": a.repeats, "repeat_seq": db.genes[int(ex[0]) if len(ex) else 0]}
 
 
 def peaks():
@@ -220,7 +234,7 @@ def reference_sample(a, db, ranges, n: int):
         if torch.cuda.is_available():
             from kaptive_b200 import workload
 
-            wl = workload.make_device_workload(db, n, a.asm_len, seed=1000, device="cuda:0", locus_ranges=ranges)
+            wl = workload.make_device_workload(db, n, a.asm_len, seed=1000, device="cuda:0", locus_ranges=ranges, **repeat_args(a, db))
             out = [wl.host_assembly(i) for i in range(n)]
             del wl
             torch.cuda.empty_cache()
@@ -303,7 +317,8 @@ def run_ours(a):
     else:
         gi = mapper.GeneIndex(db.genes, device=local)
 
-    wl = workload.make_device_workload(db, a.n_asm, a.asm_len, seed=1000, device=dev, first_index=rank * a.n_asm, locus_ranges=ranges)
+    wl = workload.make_device_workload(db, a.n_asm, a.asm_len, seed=1000, device=dev, first_index=rank * a.n_asm, locus_ranges=ranges,
+                                       **repeat_args(a, db))
     torch.cuda.synchronize()
     # the CPU leg maps the SAME first assemblies the GPU step maps: taken off the device workload before it is dropped
     cpu_cores = os.cpu_count() or 1

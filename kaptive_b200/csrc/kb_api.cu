@@ -40,6 +40,13 @@ void kb_launch_chain(const KbIndexView &, const KbBatchView &, const uint64_t *,
 void kb_launch_align(const KbIndexView &, const KbBatchView &, const KbChainRec *, int64_t, const KbGroupInfo *, const uint64_t *,
                      uint64_t *, uint8_t *, size_t, int, KbRawHit *, int64_t, uint32_t *, int64_t, unsigned long long *,
                      unsigned long long *, const int32_t *, const unsigned long long *, cudaStream_t);
+size_t kb_sort_keys64_temp_bytes(int64_t);
+cudaError_t kb_sort_keys64(void *, size_t, const uint64_t *, uint64_t *, int64_t, int, cudaStream_t);
+cudaError_t kb_rle64(void *, size_t, const uint64_t *, uint64_t *, uint32_t *, int64_t *, int64_t, cudaStream_t);
+void kb_launch_census_keys(const uint32_t *, const int32_t *, int64_t, int32_t, uint64_t *, cudaStream_t);
+size_t kb_census_hist_bytes(int);
+void kb_launch_census_quantile(const uint64_t *, const uint32_t *, const int64_t *, int64_t, uint32_t *, int, const int32_t *, int, int32_t, float,
+                               int32_t, int32_t, int32_t *, unsigned long long *, cudaStream_t);
 size_t kb_band_scratch_bytes();
 size_t kb_sizeof_job();
 size_t kb_sizeof_plan();
@@ -556,6 +563,82 @@ static int32_t census_one(const kb_index *ix, const kb_batch *bt, int asm_id, De
     return mid;
 }
 
+// The census of many assemblies (ascending ids in `list`), about a gigabase at a time: one scan over the chunks of a run of assemblies
+// dumps (hash, assembly) of every minimizer; a sort and a run-length encode give the occurrence count of every distinct minimizer, a
+// histogram of the counts per assembly its quantile (kb_census_quantile_kernel).  One stream synchronisation per group of assemblies
+// instead of three per assembly.  d_mid: n_asm entries on the device, those of the listed assemblies are overwritten.
+// d_counters[16..31] are used; [24] counts quantiles beyond the histogram (checked by the caller).  Returns the number of launches.
+static int census_many(const kb_index *ix, const kb_batch *bt, const std::vector<int32_t> &list, int32_t *d_mid, DevPool &P,
+                       unsigned long long *d_counters, cudaStream_t st)
+{
+    const kb_params_t &p = ix->host.p;
+    const KbHostBatchLayout &L = bt->L;
+    const int64_t group_bases = getenv("KAPTIVE_B200_CENSUS_GROUP") ? atoll(getenv("KAPTIVE_B200_CENSUS_GROUP")) : ((int64_t)1200 << 20);
+    auto asm_bases = [&](int a) {
+        int64_t b = 0;
+        for (int c = L.asm_ctg_start[a]; c < L.asm_ctg_start[a + 1]; ++c) b += L.ctg_len[c];
+        return b;
+    };
+    int launches = 0;
+    unsigned long long *d_over = P.get<unsigned long long>(1);
+    CU(cudaMemsetAsync(d_over, 0, 8, st));
+    size_t i = 0;
+    while (i < list.size()) {
+        // a group: listed assemblies from list[i] on, with gaps of at most 4 unlisted ones, until the bases in the range reach the limit
+        size_t j = i;
+        int a_lo = list[i], a_hi = list[i];
+        int64_t bases = asm_bases(a_lo);
+        while (j + 1 < list.size() && list[j + 1] - a_hi <= 5 && list[j + 1] - a_lo < 4096) {
+            int64_t add = 0;
+            for (int a = a_hi + 1; a <= list[j + 1]; ++a) add += asm_bases(a);
+            if (bases + add > group_bases) break;
+            bases += add, a_hi = list[j + 1], ++j;
+        }
+        const int n_list = (int)(j - i + 1), n_group = a_hi - a_lo + 1;
+        int group_bits = 1;
+        while ((1 << group_bits) < n_group) ++group_bits;
+        const int64_t n_ctg = L.asm_ctg_start[a_hi + 1] - L.asm_ctg_start[a_lo];
+        const int64_t cap = bases / 2 + 4 * n_ctg + 1024;
+        uint32_t *h = P.get<uint32_t>((size_t)cap), *cnt = P.get<uint32_t>((size_t)cap), *hist = P.get<uint32_t>(kb_census_hist_bytes(n_group) / 4);
+        int32_t *as = P.get<int32_t>((size_t)cap), *d_list = P.get<int32_t>((size_t)n_list);
+        uint64_t *k1 = P.get<uint64_t>((size_t)cap), *k2 = P.get<uint64_t>((size_t)cap);
+        int64_t *d_n = P.get<int64_t>(1);
+        const size_t tb = kb_sort_keys64_temp_bytes(cap);
+        uint8_t *tmp = P.get<uint8_t>(tb);
+        CU(cudaMemcpyAsync(d_list, list.data() + i, (size_t)n_list * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(d_counters + 16, 0, 16 * 8, st));
+        CU(cudaMemsetAsync(d_n, 0, 8, st));
+        KbBatchView v = bt->view;
+        const std::vector<int32_t> &cc = L.chunk_ctg;
+        const int64_t c0 = std::lower_bound(cc.begin(), cc.end(), L.asm_ctg_start[a_lo]) - cc.begin();
+        const int64_t c1 = std::lower_bound(cc.begin(), cc.end(), L.asm_ctg_start[a_hi + 1]) - cc.begin();
+        v.chunk_ctg += c0, v.chunk_start += c0, v.n_chunks = c1 - c0;
+        kb_launch_scan(ix->view, v, nullptr, nullptr, d_counters + 16, 0, h, as, nullptr, cap, -2, bt->n_sm, st);
+        CU(cudaGetLastError());
+        unsigned long long n_mz = 0;
+        CU(cudaMemcpyAsync(&n_mz, d_counters + 23, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((int64_t)n_mz > cap) throw std::string("census buffer overflow");
+        if (n_mz > 0) {
+            kb_launch_census_keys(h, as, (int64_t)n_mz, a_lo, k1, st);
+            CU(kb_sort_keys64(tmp, tb, k1, k2, (int64_t)n_mz, 30 + group_bits, st));
+            CU(kb_rle64(tmp, tb, k2, k1, cnt, d_n, (int64_t)n_mz, st));
+        }
+        kb_launch_census_quantile(k1, cnt, d_n, (int64_t)n_mz, hist, n_group, d_list, n_list, a_lo, p.mid_occ_frac, p.min_mid_occ, p.max_mid_occ, d_mid,
+                                  d_over, st);
+        CU(cudaGetLastError());
+        launches += 8;
+        P.release(h), P.release(cnt), P.release(hist), P.release(as), P.release(d_list), P.release(k1), P.release(k2), P.release(d_n), P.release(tmp);
+        i = j + 1;
+    }
+    unsigned long long over = 0;
+    CU(cudaMemcpyAsync(&over, d_over, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    P.release(d_over);
+    if (over) throw std::string("occurrence census: the quantile of an assembly lies beyond 65534 occurrences (internal limit)");
+    return launches;
+}
+
 static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, bool keep_stages)
 {
     if (ix->device != bt->device) return fail(KB_ERR_ARG, "index and batch live on different devices");
@@ -608,7 +691,7 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
 
         // ---------------- occurrence counts, census where needed
         std::vector<int32_t> mid_occ((size_t)n_asm, p.mid_occ > 0 ? p.mid_occ : p.min_mid_occ);
-        std::vector<int32_t> occ_skip((size_t)n_asm + 1, 0);
+        std::vector<int32_t> occ_skip((size_t)n_asm + 1, 0), census_list;
         size_t occ_words = ((size_t)n_asm * (size_t)iv.n_entries + 1) / 2 + 4;
         uint32_t *occ32 = P.get<uint32_t>(occ_words);
         int32_t *d_need = P.get<int32_t>((size_t)n_asm + 1);
@@ -626,14 +709,22 @@ static int map_batch_impl(const kb_index *ix, kb_batch *bt, kb_result **out, boo
             for (int a = 0; a < n_asm; ++a) occ_skip[(size_t)a] = need[(size_t)a] == 0 && mid_occ[(size_t)a] >= p.min_mid_occ;
             for (int a = 0; a < n_asm; ++a) {
                 if (need[(size_t)a] == 2) throw std::string("a gene minimizer occurs more than 65519 times in one assembly (limit)");
-                if (p.mid_occ <= 0 && (need[(size_t)a] || force)) {
-                    mid_occ[(size_t)a] = census_one(ix, bt, a, P, d_counters, st);
-                    launches += 4;
-                }
+                if (p.mid_occ <= 0 && (need[(size_t)a] || force)) census_list.push_back(a);
             }
         }
         int32_t *d_mid = P.get<int32_t>((size_t)n_asm + 1);
         CU(cudaMemcpyAsync(d_mid, mid_occ.data(), (size_t)n_asm * 4, cudaMemcpyHostToDevice, st));
+        if (!census_list.empty()) {
+            const char *one = getenv("KAPTIVE_B200_CENSUS_SERIAL");  // test hook: the per-assembly form
+            if (one && one[0] == '1') {
+                for (int a : census_list) mid_occ[(size_t)a] = census_one(ix, bt, a, P, d_counters, st), launches += 4;
+                CU(cudaMemcpyAsync(d_mid, mid_occ.data(), (size_t)n_asm * 4, cudaMemcpyHostToDevice, st));
+            } else {
+                launches += census_many(ix, bt, census_list, d_mid, P, d_counters, st);
+                CU(cudaMemcpyAsync(mid_occ.data(), d_mid, (size_t)n_asm * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
+        }
         // assemblies in which no gene minimizer occurs more than min_mid_occ times (and whose mid_occ is not below that floor):
         // the occurrence filter cannot fire there, the chain kernel skips its table look-ups
         int32_t *d_occ_skip = P.get<int32_t>((size_t)n_asm + 1);

@@ -153,6 +153,111 @@ cudaError_t kb_rle(void *tmp, size_t tmp_bytes, const uint32_t *in, uint32_t *un
     return cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, in, uniq, counts, n_runs, n, st);
 }
 
+// ------------------------------------------------------------------ occurrence census of many assemblies at once
+// [mm2:index.c:mm_idx_cal_max_occ] per assembly: the (1 - f) quantile of the occurrence counts of its distinct minimizers.  Keys
+// asm << 32 | hash are sorted and run-length encoded, the runs re-keyed asm << 32 | count and sorted again; one thread per assembly
+// then reads its quantile.
+size_t kb_sort_keys64_temp_bytes(int64_t n)
+{
+    size_t b = 0, b2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, n, 0, 64);
+    cub::DeviceRunLengthEncode::Encode(nullptr, b2, (const uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (int64_t *)nullptr, n);
+    return b > b2 ? b : b2;
+}
+cudaError_t kb_sort_keys64(void *tmp, size_t tmp_bytes, const uint64_t *kin, uint64_t *kout, int64_t n, int end_bit, cudaStream_t st)
+{
+    return cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, kin, kout, n, 0, end_bit, st);
+}
+cudaError_t kb_rle64(void *tmp, size_t tmp_bytes, const uint64_t *in, uint64_t *uniq, uint32_t *counts, int64_t *n_runs, int64_t n, cudaStream_t st)
+{
+    return cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, in, uniq, counts, n_runs, n, st);
+}
+// key = (assembly - a_lo) << 30 | hash: as few radix passes as the group needs
+__global__ void kb_census_key_kernel(const uint32_t *hash, const int32_t *asm_id, int64_t n, int32_t a_lo, uint64_t *key)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        key[i] = (uint64_t)(uint32_t)(asm_id[i] - a_lo) << 30 | hash[i];
+}
+// histogram of the occurrence counts >= 2 per assembly (counts of 1, nearly all of them, are what is left of the assembly's runs);
+// hist: n_group x KB_CENSUS_BINS, the last bin collects every count that does not fit
+#define KB_CENSUS_BINS 65536
+__global__ void kb_census_hist_kernel(const uint64_t *uniq, const uint32_t *counts, const int64_t *n_runs, uint32_t *hist)
+{
+    const int64_t n = *n_runs;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i];
+        if (c >= 2) atomicAdd(&hist[(uniq[i] >> 30) * KB_CENSUS_BINS + (c < KB_CENSUS_BINS - 1 ? c : KB_CENSUS_BINS - 1)], 1u);
+    }
+}
+// one WARP per listed assembly: its runs are uniq[b, e) (binary search on the assembly field), the quantile is read off the histogram
+__global__ void kb_census_quantile_kernel(const uint64_t *uniq, const int64_t *n_runs_p, const uint32_t *hist, const int32_t *asm_list, int n_list,
+                                          int32_t a_lo, float mid_occ_frac, int32_t min_mid_occ, int32_t max_mid_occ, int32_t *mid_occ,
+                                          unsigned long long *overflow)
+{
+    const int lane = threadIdx.x & 31, i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_list) return;
+    const int32_t a = asm_list[i];
+    const int64_t n_runs = *n_runs_p;
+    auto lower = [&](uint64_t v) {  // first run with key >= v
+        int64_t lo = 0, hi = n_runs;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (uniq[mid] < v) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const int64_t b = lower((uint64_t)(uint32_t)(a - a_lo) << 30), e = lower((uint64_t)((uint32_t)(a - a_lo) + 1u) << 30), n = e - b;
+    int32_t mid = INT32_MAX;  // f <= 0 or no minimizers: no cut-off
+    if (mid_occ_frac > 0.f && n > 0) {
+        int64_t kth = (int64_t)((1. - mid_occ_frac) * (double)n);
+        kth = kth > n - 1 ? n - 1 : (kth < 0 ? 0 : kth);
+        const uint32_t *h = hist + (int64_t)(a - a_lo) * KB_CENSUS_BINS;
+        // runs above the quantile: n - 1 - kth of them.  Walk the histogram from the top until more than that many runs are passed.
+        const int64_t above = n - 1 - kth;
+        int64_t passed = 0;
+        int32_t val = 1;  // every bin from 2 up holds too few runs: the quantile is a count of 1
+        for (int top = KB_CENSUS_BINS - 1; top >= 2 && val == 1; top -= 32) {
+            const int v = top - lane;
+            const uint32_t c = v >= 2 ? h[v] : 0u;
+            // inclusive prefix over lanes (lane 0 = highest count)
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, passed + (int64_t)incl > above);
+            if (hit) {
+                const int l = __ffs(hit) - 1;
+                val = top - l;
+                if (val == KB_CENSUS_BINS - 1 && lane == 0) atomicAdd(overflow, 1ull);  // the quantile itself is a count beyond the histogram
+            }
+            passed += (int64_t)__shfl_sync(0xffffffffu, incl, 31);
+        }
+        mid = val + 1;
+    }
+    if (mid < min_mid_occ) mid = min_mid_occ;
+    if (max_mid_occ > min_mid_occ && mid > max_mid_occ) mid = max_mid_occ;
+    if (lane == 0) mid_occ[a] = mid;
+}
+void kb_launch_census_keys(const uint32_t *hash, const int32_t *asm_id, int64_t n, int32_t a_lo, uint64_t *key, cudaStream_t st)
+{
+    if (n > 0) kb_census_key_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(hash, asm_id, n, a_lo, key);
+}
+size_t kb_census_hist_bytes(int n_group) { return (size_t)n_group * KB_CENSUS_BINS * 4; }
+// uniq / counts / n_runs: the run-length encoding of the sorted keys (n_runs on the device); overflow: a device counter
+void kb_launch_census_quantile(const uint64_t *uniq, const uint32_t *counts, const int64_t *n_runs, int64_t max_runs, uint32_t *hist, int n_group,
+                               const int32_t *asm_list, int n_list, int32_t a_lo, float mid_occ_frac, int32_t min_mid_occ, int32_t max_mid_occ,
+                               int32_t *mid_occ, unsigned long long *overflow, cudaStream_t st)
+{
+    cudaMemsetAsync(hist, 0, kb_census_hist_bytes(n_group), st);
+    if (max_runs > 0) kb_census_hist_kernel<<<(unsigned)std::min<int64_t>((max_runs + 255) / 256, 148 * 16), 256, 0, st>>>(uniq, counts, n_runs, hist);
+    if (n_list > 0)
+        kb_census_quantile_kernel<<<(unsigned)((n_list * 32 + 127) / 128), 128, 0, st>>>(uniq, n_runs, hist, asm_list, n_list, a_lo, mid_occ_frac,
+                                                                                        min_mid_occ, max_mid_occ, mid_occ, overflow);
+}
+
 // ------------------------------------------------------------------ chaining: one thread per group
 __global__ void __launch_bounds__(128) kb_chain_kernel(KbIndexView ix, KbBatchView bt, const uint64_t *skey, const uint32_t *sval,
                                                        const int64_t *gstart, int64_t n_groups, int64_t n_anchors,

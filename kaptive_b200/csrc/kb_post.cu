@@ -346,6 +346,118 @@ __global__ void gotoh_counts_kernel(const uint8_t *q, const int64_t *q_off, cons
     int32_t *r = res + (int64_t)idx * 4;
     r[0] = max_score, r[1] = (int32_t)(max_cnt & 0x1fffff), r[2] = (int32_t)((max_cnt >> 21) & 0x1fffff), r[3] = (int32_t)(max_cnt >> 42);
 }
+
+// The same DP, one WARP per pair, row state in registers.  Lane l holds the K band slots b = l K .. l K + K - 1 of the current row
+// (slot b of row i is column j = i - kl + b, so (i - 1, j - 1) is the same slot of the previous row and (i - 1, j) the next one: one
+// shuffle per quantity and row).  The horizontal gap state, the only dependency along a row, is a prefix maximum: opening from a cell
+// that was itself reached by a horizontal gap never beats extending that gap (gap_open > 0), so
+//     I(b) = max over b' < b of [ max(M'(b'), 0) - go - ge (b - b') ],   M' = max(diagonal, vertical) as the reference computes it,
+// where ties go to the nearest b' (the reference prefers "open" on ties) and the cell left of the band counts as M = 0; the counts
+// ride along as (count - gaps * b').  A warp scan (5 shuffle steps) gives every lane the prefix of the lanes before it.  The best
+// cell is the first one in row-major order with the highest score, as in the sequential loop.  Pairs with more than 32 K band slots
+// or a target longer than GW_TMAX stay with the thread-per-pair kernel.
+#define GW_TMAX 2048
+template <int K>
+__global__ void __launch_bounds__(128) gotoh_counts_warp_kernel(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t,
+                                                                const int64_t *t_off, const int32_t *t_len, int32_t first, int32_t n_end, int32_t k,
+                                                                int32_t go, int32_t ge, const int32_t *perm, int32_t *res)
+{
+    __shared__ int8_t s_aa[256], s_bl[625];
+    __shared__ uint8_t s_t[4][GW_TMAX + 8];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_aa[x] = c_tab.aa_idx[x];
+    for (int x = threadIdx.x; x < 625; x += blockDim.x) s_bl[x] = c_tab.blosum[x];
+    __syncthreads();
+    typedef unsigned long long u64;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t nw = (int64_t)gridDim.x * 4;
+    const int32_t INF = -1000000000;
+    const u64 ONE_M = 1ull, ONE_X = 1ull << 21, ONE_G = 1ull << 42;
+    const unsigned FULL = 0xffffffffu;
+    for (int64_t pi = first + (int64_t)blockIdx.x * 4 + wi; pi < n_end; pi += nw) {
+        const int idx = perm[pi];
+        const uint8_t *s1 = q + q_off[idx], *s2 = t + t_off[idx];
+        const int32_t len1 = q_len[idx], len2 = t_len[idx], rows = len1 + 1, cols = len2 + 1;
+        const int32_t dl = len1 > len2 ? len1 - len2 : len2 - len1;
+        const int32_t kl = k > dl + 1 ? k : dl + 1, nslots = 2 * kl + 1;
+        __syncwarp();
+        for (int x = lane; x < len2; x += 32) s_t[wi][x] = s2[x];
+        __syncwarp();
+        int32_t Mp[K], Dp[K];
+        u64 CMp[K], CDp[K];
+#pragma unroll
+        for (int m = 0; m < K; ++m) Mp[m] = 0, Dp[m] = INF, CMp[m] = 0, CDp[m] = 0;  // row 0: M = 0, no vertical gap
+        int32_t best_s = 0, best_pos = 0x7fffffff;
+        u64 best_c = 0;
+        uint8_t a_next = rows > 1 ? s1[0] : 0;
+        for (int32_t i = 1; i < rows; ++i) {
+            const uint8_t a = a_next;
+            if (i + 1 < rows) a_next = s1[i];
+            const int32_t ai = s_aa[a], o = i - kl;
+            int32_t nM = __shfl_down_sync(FULL, Mp[0], 1), nD = __shfl_down_sync(FULL, Dp[0], 1);
+            u64 nCM = __shfl_down_sync(FULL, CMp[0], 1), nCD = __shfl_down_sync(FULL, CDp[0], 1);
+            if (lane == 31) nM = 0, nD = INF, nCM = 0, nCD = 0;
+            int32_t Mq[K], Dn[K], key[K];
+            u64 CMq[K], CDn[K], cadj[K];
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const int32_t b = lane * K + m, j = o + b;
+                const bool valid = j >= 1 && j < cols && b < nslots;
+                const int32_t m_top = m + 1 < K ? Mp[m + 1 < K ? m + 1 : 0] : nM, d_top = m + 1 < K ? Dp[m + 1 < K ? m + 1 : 0] : nD;
+                const u64 cm_top = m + 1 < K ? CMp[m + 1 < K ? m + 1 : 0] : nCM, cd_top = m + 1 < K ? CDp[m + 1 < K ? m + 1 : 0] : nCD;
+                const int32_t d_open = m_top - go - ge, d_ext = d_top - ge;
+                int32_t dcur;
+                u64 cd;
+                if (d_open >= d_ext) dcur = d_open, cd = cm_top + ONE_G;
+                else dcur = d_ext, cd = cd_top + ONE_G;
+                const uint8_t br = valid ? s_t[wi][j - 1] : (uint8_t)0;
+                const int32_t bi = s_aa[br];
+                const int32_t sub = (ai >= 0 && bi >= 0) ? (int32_t)s_bl[ai * 25 + bi] : -128;
+                int32_t best = Mp[m] + sub;
+                u64 cb = CMp[m] + (a == br ? ONE_M : ONE_X);
+                if (dcur > best) best = dcur, cb = cd;
+                Mq[m] = best, CMq[m] = cb, Dn[m] = dcur, CDn[m] = cd;
+                const bool pos = valid && best > 0;  // what a horizontal gap can open from: the cell's M unless the gap state itself wins there
+                key[m] = (pos ? best : 0) + ge * b, cadj[m] = (pos ? cb : 0ull) - ONE_G * (u64)(int64_t)b;
+            }
+            int32_t ak = key[0];
+            u64 ac = cadj[0];
+#pragma unroll
+            for (int m = 1; m < K; ++m)
+                if (key[m] >= ak) ak = key[m], ac = cadj[m];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t ok = __shfl_up_sync(FULL, ak, d);
+                const u64 oc = __shfl_up_sync(FULL, ac, d);
+                if (lane >= d && ok > ak) ak = ok, ac = oc;
+            }
+            int32_t run_k = __shfl_up_sync(FULL, ak, 1);
+            u64 run_c = __shfl_up_sync(FULL, ac, 1);
+            if (lane == 0 || -ge > run_k) run_k = -ge, run_c = ONE_G;  // the cell left of the band (slot -1): M = 0, no counts
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const int32_t b = lane * K + m, j = o + b;
+                const bool valid = j >= 1 && j < cols && b < nslots;
+                const int32_t icur = run_k - go - ge * b;
+                const u64 ci = run_c + ONE_G * (u64)(int64_t)b;
+                int32_t best = Mq[m];
+                u64 cb = CMq[m];
+                if (icur > best) best = icur, cb = ci;
+                if (valid && best > best_s) best_s = best, best_c = cb, best_pos = i * cols + j;
+                const bool keep = valid && best > 0;
+                Mp[m] = keep ? best : 0, CMp[m] = keep ? cb : 0ull;
+                Dp[m] = valid ? Dn[m] : INF, CDp[m] = valid ? CDn[m] : 0ull;
+                if (key[m] >= run_k) run_k = key[m], run_c = cadj[m];
+            }
+        }
+        // the first cell in row-major order among those with the highest score
+        const int32_t top = __reduce_max_sync(FULL, best_s);
+        const int32_t wpos = __reduce_min_sync(FULL, best_s == top ? best_pos : 0x7fffffff);
+        if (best_s == top && best_pos == wpos) {
+            int32_t *r = res + (int64_t)idx * 4;
+            r[0] = best_s, r[1] = (int32_t)(best_c & 0x1fffff), r[2] = (int32_t)((best_c >> 21) & 0x1fffff), r[3] = (int32_t)(best_c >> 42);
+        }
+    }
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -627,37 +739,55 @@ int kb_post_type_numerics(const KbBatchView &bv, int device, const int32_t *ctg,
         PCU(cudaMemcpyAsync(prot_len, d_pl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         PCU(cudaStreamSynchronize(st));  // the band of every pair depends on the length of its translated hit
         const double t_tr = dbg ? now_ms() : 0;
-        // pairs sorted by band width (widest first); a warp's tile is as wide as its widest pair
+        // pairs sorted by band width (widest first).  Those with at most 128 band slots and a target of at most GW_TMAX residues go to the
+        // warp-per-pair kernel; the rest (listed first) to the thread-per-pair kernel, where a warp's tile is as wide as its widest pair
         std::vector<int32_t> bwv((size_t)n), perm((size_t)n);
+        std::vector<uint8_t> thr((size_t)n);
+        const bool use_warp = go > 0 && ge > 0 && !(getenv("KAPTIVE_B200_GOTOH_WARP") && getenv("KAPTIVE_B200_GOTOH_WARP")[0] == '0');
         for (int64_t i = 0; i < n; ++i) {
             const int32_t l1 = prot_len[i], l2 = h_trans_len[gene[i]];
             const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1;
-            // a pair's rows are min(band, work) wide at most; its cost is rows x band: sort key = band, ties by query length
             bwv[(size_t)i] = (int32_t)(2 * kl + 3);
+            thr[(size_t)i] = !use_warp || 2 * kl + 1 > 128 || l2 > GW_TMAX;
             t_len[(size_t)i] = l2, t_off[(size_t)i] = table[(size_t)gene[i]];
             perm[(size_t)i] = (int32_t)i;
         }
         std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) {
+            if (thr[(size_t)x] != thr[(size_t)y]) return thr[(size_t)x] > thr[(size_t)y];
             if (bwv[(size_t)x] != bwv[(size_t)y]) return bwv[(size_t)x] > bwv[(size_t)y];
             return prot_len[x] > prot_len[y];
         });
-        const int64_t n_warp = (n + 31) / 32;
-        std::vector<int64_t> tile_off((size_t)n_warp);
-        std::vector<int32_t> tile_bw((size_t)n_warp);
+        int64_t n_thr = 0, n_k4 = 0;  // perm[0, n_thr): thread kernel; [n_thr, n_thr + n_k4): more than 64 band slots; the rest: at most 64
+        for (int64_t i = 0; i < n; ++i) {
+            if (thr[(size_t)i]) ++n_thr;
+            else if (bwv[(size_t)i] - 2 > 64) ++n_k4;
+        }
+        const int64_t n_warp = (n_thr + 31) / 32;
+        std::vector<int64_t> tile_off((size_t)n_warp + 1);
+        std::vector<int32_t> tile_bw((size_t)n_warp + 1);
         int64_t row_total = 0;  // in elements of one array
         for (int64_t w = 0; w < n_warp; ++w) {
             tile_bw[(size_t)w] = bwv[(size_t)perm[(size_t)(w * 32)]];
             tile_off[(size_t)w] = row_total, row_total += (int64_t)tile_bw[(size_t)w] * 32;
         }
         (void)row_off;
-        const int64_t *d_to = (const int64_t *)up(t_off.data(), (size_t)n * 8), *d_tile = (const int64_t *)up(tile_off.data(), (size_t)n_warp * 8);
+        const int64_t *d_to = (const int64_t *)up(t_off.data(), (size_t)n * 8), *d_tile = (const int64_t *)up(tile_off.data(), ((size_t)n_warp + 1) * 8);
         const int32_t *d_tl = (const int32_t *)up(t_len.data(), (size_t)n * 4), *d_perm = (const int32_t *)up(perm.data(), (size_t)n * 4);
-        const int32_t *d_tbw = (const int32_t *)up(tile_bw.data(), (size_t)n_warp * 4);
+        const int32_t *d_tbw = (const int32_t *)up(tile_bw.data(), ((size_t)n_warp + 1) * 4);
         int32_t *d_rows = (int32_t *)dalloc((size_t)row_total * 4 * 4), *d_res = (int32_t *)dalloc((size_t)n * 16);
         unsigned long long *d_cnt = (unsigned long long *)dalloc((size_t)row_total * 4 * 8);
         const double t_prep = dbg ? now_ms() : 0;
-        gotoh_counts_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)n, k, go, ge, d_perm, d_tile, d_tbw,
-                                                                     d_rows, d_cnt, d_res);
+        if (n_thr > 0)
+            gotoh_counts_kernel<<<(unsigned)((n_thr + 63) / 64), 64, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)n_thr, k, go, ge, d_perm, d_tile,
+                                                                             d_tbw, d_rows, d_cnt, d_res);
+        {
+            const int64_t a4 = n_thr, b4 = n_thr + n_k4;
+            auto grid = [](int64_t pairs) { return (unsigned)std::min<int64_t>((pairs + 3) / 4, 148 * 16); };
+            if (b4 > a4)
+                gotoh_counts_warp_kernel<4><<<grid(b4 - a4), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)a4, (int32_t)b4, k, go, ge, d_perm, d_res);
+            if (n > b4)
+                gotoh_counts_warp_kernel<2><<<grid(n - b4), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)b4, (int32_t)n, k, go, ge, d_perm, d_res);
+        }
         PCU(cudaGetLastError());
         std::vector<int32_t> r4((size_t)n * 4);
         PCU(cudaMemcpyAsync(r4.data(), d_res, (size_t)n * 16, cudaMemcpyDeviceToHost, st));

@@ -257,9 +257,13 @@ __global__ void __launch_bounds__(128, KB_SCAN_CTAS) kb_scan_kernel(KbIndexView 
                 uint32_t hx = have ? Q.x[qslot] : 0, hy = have ? Q.y[qslot] : 0;
                 uint32_t est = 0, ecnt = 0;
                 bool hit = have && kb_ht_lookup(ix.ht, ix.ht_mask, hx, &est, &ecnt);
-                if (mz_hash && have && asm_id == mz_asm) {  // debug / parity dump of one assembly's minimizers
+                if (mz_hash && have && (asm_id == mz_asm || mz_asm == -2)) {
+                    // minimizer dump: one assembly with contig / position (parity tests), or every chunk given with the assembly id (census)
                     unsigned long long o = atomicAdd(&counters[7], 1ull);
-                    if ((int64_t)o < mz_cap) mz_hash[o] = hx, mz_ctg[o] = ctg - bt.asm_ctg_start[asm_id], mz_pos[o] = hy;
+                    if ((int64_t)o < mz_cap) {
+                        mz_hash[o] = hx, mz_ctg[o] = mz_asm == -2 ? asm_id : ctg - bt.asm_ctg_start[asm_id];
+                        if (mz_pos) mz_pos[o] = hy;
+                    }
                 }
                 uint32_t cnt = hit ? ecnt : 0;
                 // warp-aggregated slot allocation

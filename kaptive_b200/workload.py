@@ -40,10 +40,15 @@ class DeviceWorkload:
 def make_device_workload(db: synth.SynthDB, n_asm: int, asm_len: int = 5_000_000, mean_contigs: float = 80.0,
                          seed: int = 1000, device: str = "cuda:0", gc: float = 0.57, n_frac: float = 1e-4,
                          sub: tuple[float, float] = (0.0, 0.05), indel: tuple[float, float] = (0.0, 0.005),
-                         first_index: int = 0, locus_ranges: tuple[tuple[int, int], ...] | None = None) -> DeviceWorkload:
+                         first_index: int = 0, locus_ranges: tuple[tuple[int, int], ...] | None = None, repeats: int = 0,
+                         repeat_seq: bytes | None = None) -> DeviceWorkload:
     """Assembly `first_index + a` is a pure function of (seed, first_index + a, asm_len): the background is drawn in fixed chunks
     of `step` assemblies whose generator seed depends on the chunk's first global index only, so a rank, a smaller sample (the CPU
-    arm) and the full batch all see the same sequences for the same global assembly index."""
+    arm) and the full batch all see the same sequences for the same global assembly index.
+
+    repeats > 0 writes that many copies of `repeat_seq` (an insertion-sequence-like element; either strand) into every assembly,
+    away from the embedded loci: when the element is also a database gene, its minimizers occur more often than minimap2's
+    min_mid_occ floor and every assembly takes the occurrence-census path (mm_idx_cal_max_occ)."""
     import torch
 
     dev = torch.device(device)
@@ -89,6 +94,17 @@ def make_device_workload(db: synth.SynthDB, n_asm: int, asm_len: int = 5_000_000
                     break
             taken.append((pos, pos + len(ls)))
             out[a * asm_len + pos : a * asm_len + pos + len(ls)] = torch.from_numpy(ls.copy()).to(dev)
+        if repeats > 0 and repeat_seq:
+            rr = np.random.default_rng((seed + first_index + a) * 7919 + 13)  # its own stream: the rest of the assembly does not change
+            el = np.frombuffer(repeat_seq, dtype=np.uint8)
+            for _ in range(repeats):
+                cp = synth.revcomp(el) if rr.random() < 0.5 else el
+                while True:
+                    pos = int(rr.integers(0, asm_len - len(cp)))
+                    if all(pos + len(cp) <= s0 or pos >= s1 for s0, s1 in taken):
+                        break
+                taken.append((pos, pos + len(cp)))
+                out[a * asm_len + pos : a * asm_len + pos + len(cp)] = torch.from_numpy(cp.copy()).to(dev)
         n_ctg = max(1, int(rng.poisson(mean_contigs)))
         bps = np.unique(rng.integers(1, asm_len, size=n_ctg - 1)) if n_ctg > 1 else np.zeros(0, dtype=np.int64)
         bounds = np.concatenate([[0], bps, [asm_len]]).astype(np.int64)

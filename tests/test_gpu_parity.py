@@ -411,3 +411,32 @@ def test_one_warp_per_chain_kernel_alone_gives_the_same_hits(env, monkeypatch):
     assert res.counters["slow_chains"] == 0  # the staged path did not run at all
     for ai, n in enumerate(names):
         check_against(res, ai, GOLD[f"{n}/hits"], GOLD[f"{n}/cigar"])
+
+
+def test_batched_census_equals_the_per_assembly_census(monkeypatch):
+    """Assemblies that carry 14 copies of a database gene take the occurrence census (mm_idx_cal_max_occ).  The batched form (one scan,
+    two sorts and a run-length encode per group of assemblies) gives every assembly the mid_occ of the per-assembly form, groups of
+    every size included, and the hits do not change."""
+    import torch
+
+    from kaptive_b200 import mapper, synth, workload
+
+    db = synth.make_db(n_loci=6, genes_per_locus=6, n_core=1, seed=5)
+    wl = workload.make_device_workload(db, 9, 300_000, mean_contigs=6, seed=77, device="cuda:0", repeats=14, repeat_seq=db.genes[3])
+    gi = mapper.GeneIndex(db.genes, device=0)
+    batch = mapper.AssemblyBatch(wl.ascii.data_ptr(), wl.contig_off, wl.contig_len, wl.asm_contig_start, device=0)
+    results = {}
+    for name, env in (("serial", {"KAPTIVE_B200_CENSUS_SERIAL": "1"}), ("batched", {}), ("small groups", {"KAPTIVE_B200_CENSUS_GROUP": "700000"})):
+        for k in ("KAPTIVE_B200_CENSUS_SERIAL", "KAPTIVE_B200_CENSUS_GROUP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = gi.map(batch)
+        results[name] = (np.array(r.mid_occ), {k: np.array(v) for k, v in r.hits.items()}, np.array(r.cigar))
+    torch.cuda.synchronize()
+    ref = results["serial"]
+    assert len(ref[1]["gene"]) > 0 and (ref[0] >= 10).all()
+    for name in ("batched", "small groups"):
+        got = results[name]
+        assert np.array_equal(got[0], ref[0]), (name, got[0], ref[0])
+        assert all(np.array_equal(got[1][k], ref[1][k]) for k in ref[1]) and np.array_equal(got[2], ref[2]), name
