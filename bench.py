@@ -494,6 +494,13 @@ def run_ours(a):
     typed_value = a.n_asm * world / (float(tt[0]) / a.steps)
     typed_info = {"type_many_ms_per_step": float(tt[1]) / a.steps * 1e3, "typeable": int(typed.typeable.sum()), "gene_hits": int(len(typed.gene_hits["gene"])),
                   "best_locus_is_the_embedded_k_locus": int((typed.best_locus == wl.locus[:, 0]).sum())}
+    try:  # where the last type_many spent its time inside the library (seconds -> ms)
+        t4 = (C.c_double * 4)()
+        L.kb_type_debug_times(t4)
+        typed_info["last_call_ms"] = {"pass1_cull_cluster_pieces": round(t4[0] * 1e3, 1), "job_list": round(t4[1] * 1e3, 1),
+                                      "device_translate_gotoh": round(t4[2] * 1e3, 1), "pass2_states_confidence": round(t4[3] * 1e3, 1)}
+    except Exception:
+        pass
 
     # end-to-end (host buffers) ------------------------------------------------------------------
     pbe = ingest.PackedBatch(pin_seq2.numpy().view(np.uint32), pin_mask.numpy().view(np.uint32), e_len, e_soff, e_acs, int(st_e.value), [])

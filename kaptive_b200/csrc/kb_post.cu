@@ -458,6 +458,132 @@ __global__ void __launch_bounds__(128) gotoh_counts_warp_kernel(const uint8_t *q
         }
     }
 }
+
+// The same recurrences for WIDE bands (a translated hit much shorter or longer than the database protein: band = twice the length
+// difference): one warp per pair, the row state of all band slots in shared memory, a row processed in chunks of 64 slots from left
+// to right (two slots per lane; the horizontal-gap prefix of a chunk continues from the last lane of the chunk before).  The state
+// is updated in place: slot b of row i needs slots b and b + 1 of row i - 1, which a chunk reads before it writes and which later
+// chunks have not touched yet.  Slots outside the matrix are never written and keep the "no cell" state they start with.
+// Dynamic shared memory per warp: (slot_cap + 2) x 24 bytes + GW_TMAX + 8.
+__global__ void __launch_bounds__(128) gotoh_counts_wide_kernel(const uint8_t *q, const int64_t *q_off, const int32_t *q_len, const uint8_t *t,
+                                                                const int64_t *t_off, const int32_t *t_len, int32_t first, int32_t n_end, int32_t k,
+                                                                int32_t go, int32_t ge, const int32_t *perm, int32_t slot_cap, int32_t *res)
+{
+    __shared__ int8_t s_aa[256], s_bl[625];
+    extern __shared__ __align__(16) uint8_t gw_dyn[];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_aa[x] = c_tab.aa_idx[x];
+    for (int x = threadIdx.x; x < 625; x += blockDim.x) s_bl[x] = c_tab.blosum[x];
+    __syncthreads();
+    typedef unsigned long long u64;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int64_t nw = (int64_t)gridDim.x * wpc;
+    const size_t per_warp = (size_t)(slot_cap + 2) * 24 + GW_TMAX + 8;
+    uint8_t *base = gw_dyn + (size_t)wi * per_warp;
+    u64 *CM = reinterpret_cast<u64 *>(base), *CD = CM + (slot_cap + 2);
+    int32_t *M = reinterpret_cast<int32_t *>(CD + (slot_cap + 2)), *D = M + (slot_cap + 2);
+    uint8_t *s_t = reinterpret_cast<uint8_t *>(D + (slot_cap + 2));
+    const int32_t INF = -1000000000;
+    const u64 ONE_M = 1ull, ONE_X = 1ull << 21, ONE_G = 1ull << 42;
+    const unsigned FULL = 0xffffffffu;
+    for (int64_t pi = first + (int64_t)blockIdx.x * wpc + wi; pi < n_end; pi += nw) {
+        const int idx = perm[pi];
+        const uint8_t *s1 = q + q_off[idx], *s2 = t + t_off[idx];
+        const int32_t len1 = q_len[idx], len2 = t_len[idx], rows = len1 + 1, cols = len2 + 1;
+        const int32_t dl = len1 > len2 ? len1 - len2 : len2 - len1;
+        const int32_t kl = k > dl + 1 ? k : dl + 1, nslots = 2 * kl + 1;
+        __syncwarp();
+        for (int x = lane; x < len2; x += 32) s_t[x] = s2[x];
+        for (int x = lane; x < nslots + 2; x += 32) M[x] = 0, D[x] = INF, CM[x] = 0, CD[x] = 0;
+        __syncwarp();
+        int32_t best_s = 0, best_pos = 0x7fffffff;
+        u64 best_c = 0;
+        uint8_t a_next = rows > 1 ? s1[0] : 0;
+        for (int32_t i = 1; i < rows; ++i) {
+            const uint8_t a = a_next;
+            if (i + 1 < rows) a_next = s1[i];
+            const int32_t ai = s_aa[a], o = i - kl;
+            int32_t b_lo = 1 - o > 0 ? 1 - o : 0, b_hi = cols - 1 - o < nslots - 1 ? cols - 1 - o : nslots - 1;  // valid slots of this row
+            if (b_hi < b_lo) continue;
+            // the cell left of the first valid one counts as M = 0 without counts
+            int32_t run_k = ge * (b_lo - 1);
+            u64 run_c = 0ull - ONE_G * (u64)(int64_t)(b_lo - 1);
+            for (int32_t cb0 = b_lo; cb0 <= b_hi; cb0 += 64) {
+                const int32_t b0 = cb0 + 2 * lane;
+                int32_t pm[3], pd[3];
+                u64 pcm[3], pcd[3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const int32_t b = b0 + x < nslots + 1 ? b0 + x : nslots + 1;  // slots nslots, nslots + 1: never written ("no cell")
+                    pm[x] = M[b], pd[x] = D[b], pcm[x] = CM[b], pcd[x] = CD[b];
+                }
+                __syncwarp();
+                int32_t Mq[2], Dn[2], key[2];
+                u64 CMq[2], CDn[2], cadj[2];
+                bool valid[2];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int32_t b = b0 + m, j = o + b;
+                    valid[m] = b <= b_hi;
+                    const int32_t d_open = pm[m + 1] - go - ge, d_ext = pd[m + 1] - ge;
+                    int32_t dcur;
+                    u64 cd;
+                    if (d_open >= d_ext) dcur = d_open, cd = pcm[m + 1] + ONE_G;
+                    else dcur = d_ext, cd = pcd[m + 1] + ONE_G;
+                    const uint8_t br = valid[m] ? s_t[j - 1] : (uint8_t)0;
+                    const int32_t bi = s_aa[br];
+                    const int32_t sub = (ai >= 0 && bi >= 0) ? (int32_t)s_bl[ai * 25 + bi] : -128;
+                    int32_t best = pm[m] + sub;
+                    u64 cb = pcm[m] + (a == br ? ONE_M : ONE_X);
+                    if (dcur > best) best = dcur, cb = cd;
+                    Mq[m] = best, CMq[m] = cb, Dn[m] = dcur, CDn[m] = cd;
+                    const bool pos = valid[m] && best > 0;
+                    key[m] = valid[m] ? (pos ? best : 0) + ge * b : INF;  // slots past the row's end: never a source
+                    cadj[m] = (pos ? cb : 0ull) - ONE_G * (u64)(int64_t)b;
+                }
+                int32_t ak = key[0];
+                u64 ac = cadj[0];
+                if (key[1] >= ak) ak = key[1], ac = cadj[1];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t ok = __shfl_up_sync(FULL, ak, d);
+                    const u64 oc = __shfl_up_sync(FULL, ac, d);
+                    if (lane >= d && ok > ak) ak = ok, ac = oc;
+                }
+                int32_t ek = __shfl_up_sync(FULL, ak, 1);
+                u64 ec = __shfl_up_sync(FULL, ac, 1);
+                if (lane == 0 || run_k > ek) ek = run_k, ec = run_c;  // what came before this chunk wins only when strictly better
+                // the prefix after this chunk, for the next one
+                {
+                    const int32_t lk = __shfl_sync(FULL, ak, 31);
+                    const u64 lc = __shfl_sync(FULL, ac, 31);
+                    if (lk >= run_k) run_k = lk, run_c = lc;
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int32_t b = b0 + m, j = o + b;
+                    const int32_t icur = ek - go - ge * b;
+                    const u64 ci = ec + ONE_G * (u64)(int64_t)b;
+                    int32_t best = Mq[m];
+                    u64 cb = CMq[m];
+                    if (icur > best) best = icur, cb = ci;
+                    if (valid[m]) {
+                        if (best > best_s) best_s = best, best_c = cb, best_pos = i * cols + j;
+                        const bool keep = best > 0;
+                        M[b] = keep ? best : 0, CM[b] = keep ? cb : 0ull, D[b] = Dn[m], CD[b] = CDn[m];
+                    }
+                    if (key[m] >= ek) ek = key[m], ec = cadj[m];
+                }
+                __syncwarp();
+            }
+        }
+        const int32_t top = __reduce_max_sync(FULL, best_s);
+        const int32_t wpos = __reduce_min_sync(FULL, best_s == top ? best_pos : 0x7fffffff);
+        if (best_s == top && best_pos == wpos) {
+            int32_t *r = res + (int64_t)idx * 4;
+            r[0] = best_s, r[1] = (int32_t)(best_c & 0x1fffff), r[2] = (int32_t)((best_c >> 21) & 0x1fffff), r[3] = (int32_t)(best_c >> 42);
+        }
+    }
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -739,36 +865,53 @@ int kb_post_type_numerics(const KbBatchView &bv, int device, const int32_t *ctg,
         PCU(cudaMemcpyAsync(prot_len, d_pl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         PCU(cudaStreamSynchronize(st));  // the band of every pair depends on the length of its translated hit
         const double t_tr = dbg ? now_ms() : 0;
-        // pairs sorted by band width (widest first).  Those with at most 128 band slots and a target of at most GW_TMAX residues go to the
-        // warp-per-pair kernel; the rest (listed first) to the thread-per-pair kernel, where a warp's tile is as wide as its widest pair
+        // pairs by kernel, then by band width (widest first): 0 = thread per pair (more than 2048 band slots or a target over GW_TMAX residues:
+        // a warp's tile is as wide as its widest pair), 1 / 2 / 3 = warp per pair with the row state in shared memory (up to 2048 / 1024 / 512
+        // slots: 1 / 2 / 3 CTAs per SM), 4 / 5 = warp per pair with the row state in registers (up to 128 / 64 slots)
         std::vector<int32_t> bwv((size_t)n), perm((size_t)n);
-        std::vector<uint8_t> thr((size_t)n);
+        std::vector<uint8_t> cls((size_t)n);
         const bool use_warp = go > 0 && ge > 0 && !(getenv("KAPTIVE_B200_GOTOH_WARP") && getenv("KAPTIVE_B200_GOTOH_WARP")[0] == '0');
+        int64_t n_cls[6] = {0, 0, 0, 0, 0, 0};
         for (int64_t i = 0; i < n; ++i) {
             const int32_t l1 = prot_len[i], l2 = h_trans_len[gene[i]];
-            const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1;
+            const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1, kl = k > dl + 1 ? k : dl + 1, slots = 2 * kl + 1;
             bwv[(size_t)i] = (int32_t)(2 * kl + 3);
-            thr[(size_t)i] = !use_warp || 2 * kl + 1 > 128 || l2 > GW_TMAX;
+            const int c = (!use_warp || slots > 2048 || l2 > GW_TMAX) ? 0 : (slots > 1024 ? 1 : (slots > 512 ? 2 : (slots > 128 ? 3 : (slots > 64 ? 4 : 5))));
+            cls[(size_t)i] = (uint8_t)c, ++n_cls[c];
             t_len[(size_t)i] = l2, t_off[(size_t)i] = table[(size_t)gene[i]];
             perm[(size_t)i] = (int32_t)i;
         }
-        std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) {
-            if (thr[(size_t)x] != thr[(size_t)y]) return thr[(size_t)x] > thr[(size_t)y];
-            if (bwv[(size_t)x] != bwv[(size_t)y]) return bwv[(size_t)x] > bwv[(size_t)y];
-            return prot_len[x] > prot_len[y];
-        });
-        int64_t n_thr = 0, n_k4 = 0;  // perm[0, n_thr): thread kernel; [n_thr, n_thr + n_k4): more than 64 band slots; the rest: at most 64
-        for (int64_t i = 0; i < n; ++i) {
-            if (thr[(size_t)i]) ++n_thr;
-            else if (bwv[(size_t)i] - 2 > 64) ++n_k4;
+        {
+            // order: kernel class, then band width and hit length descending (the balance of the kernels needs no finer order than 4096
+            // steps of either); a stable three-pass radix sort of 27-bit keys instead of a comparison sort of 300,000 pairs
+            std::vector<uint32_t> key((size_t)n), key2((size_t)n);
+            std::vector<int32_t> perm2((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                const uint32_t b = (uint32_t)std::min<int32_t>(bwv[(size_t)i], 4095), l = (uint32_t)std::min<int32_t>(std::max<int32_t>(prot_len[i], 0), 4095);
+                key[(size_t)i] = (uint32_t)cls[(size_t)i] << 24 | (4095u - b) << 12 | (4095u - l);
+            }
+            for (int pass = 0; pass < 3; ++pass) {
+                const int sh = 9 * pass;
+                int64_t cnt[513] = {0};
+                for (int64_t i = 0; i < n; ++i) ++cnt[((key[(size_t)i] >> sh) & 511u) + 1];
+                for (int x = 0; x < 512; ++x) cnt[x + 1] += cnt[x];
+                for (int64_t i = 0; i < n; ++i) {
+                    const int64_t o = cnt[(key[(size_t)i] >> sh) & 511u]++;
+                    key2[(size_t)o] = key[(size_t)i], perm2[(size_t)o] = perm[(size_t)i];
+                }
+                key.swap(key2), perm.swap(perm2);
+            }
         }
+        const int64_t n_thr = n_cls[0];
         const int64_t n_warp = (n_thr + 31) / 32;
         std::vector<int64_t> tile_off((size_t)n_warp + 1);
         std::vector<int32_t> tile_bw((size_t)n_warp + 1);
         int64_t row_total = 0;  // in elements of one array
         for (int64_t w = 0; w < n_warp; ++w) {
-            tile_bw[(size_t)w] = bwv[(size_t)perm[(size_t)(w * 32)]];
-            tile_off[(size_t)w] = row_total, row_total += (int64_t)tile_bw[(size_t)w] * 32;
+            int32_t widest = 0;
+            for (int64_t x = w * 32; x < std::min<int64_t>(n_thr, w * 32 + 32); ++x) widest = std::max(widest, bwv[(size_t)perm[(size_t)x]]);
+            tile_bw[(size_t)w] = widest;
+            tile_off[(size_t)w] = row_total, row_total += (int64_t)widest * 32;
         }
         (void)row_off;
         const int64_t *d_to = (const int64_t *)up(t_off.data(), (size_t)n * 8), *d_tile = (const int64_t *)up(tile_off.data(), ((size_t)n_warp + 1) * 8);
@@ -781,20 +924,39 @@ int kb_post_type_numerics(const KbBatchView &bv, int device, const int32_t *ctg,
             gotoh_counts_kernel<<<(unsigned)((n_thr + 63) / 64), 64, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)n_thr, k, go, ge, d_perm, d_tile,
                                                                              d_tbw, d_rows, d_cnt, d_res);
         {
-            const int64_t a4 = n_thr, b4 = n_thr + n_k4;
-            auto grid = [](int64_t pairs) { return (unsigned)std::min<int64_t>((pairs + 3) / 4, 148 * 16); };
-            if (b4 > a4)
-                gotoh_counts_warp_kernel<4><<<grid(b4 - a4), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)a4, (int32_t)b4, k, go, ge, d_perm, d_res);
-            if (n > b4)
-                gotoh_counts_warp_kernel<2><<<grid(n - b4), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)b4, (int32_t)n, k, go, ge, d_perm, d_res);
+            auto grid = [](int64_t pairs, int per_sm) { return (unsigned)std::min<int64_t>((pairs + 3) / 4, 148 * (int64_t)per_sm); };
+            int64_t lo = n_thr;
+            for (int c = 1; c <= 3; ++c) {  // wide bands: shared-memory rows
+                const int64_t hi = lo + n_cls[c];
+                if (hi > lo) {
+                    const int slot_cap = c == 1 ? 2048 : (c == 2 ? 1024 : 512);
+                    const size_t smem = 4 * ((size_t)(slot_cap + 2) * 24 + GW_TMAX + 8);
+                    static bool attr_set[4] = {false, false, false, false};
+                    if (!attr_set[c]) {
+                        PCU(cudaFuncSetAttribute(gotoh_counts_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2050 * 24 + GW_TMAX + 8)));
+                        attr_set[c] = true;
+                    }
+                    gotoh_counts_wide_kernel<<<grid(hi - lo, c), 128, smem, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)lo, (int32_t)hi, k, go,
+                                                                                              ge, d_perm, slot_cap, d_res);
+                }
+                lo = hi;
+            }
+            if (n_cls[4] > 0)
+                gotoh_counts_warp_kernel<4><<<grid(n_cls[4], 16), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)lo, (int32_t)(lo + n_cls[4]), k, go, ge,
+                                                                               d_perm, d_res);
+            lo += n_cls[4];
+            if (n_cls[5] > 0)
+                gotoh_counts_warp_kernel<2><<<grid(n_cls[5], 16), 128, 0, st>>>(d_aa, d_ao, d_pl, d_trans, d_to, d_tl, (int32_t)lo, (int32_t)(lo + n_cls[5]), k, go, ge,
+                                                                               d_perm, d_res);
         }
         PCU(cudaGetLastError());
         std::vector<int32_t> r4((size_t)n * 4);
         PCU(cudaMemcpyAsync(r4.data(), d_res, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
         PCU(cudaStreamSynchronize(st));
         if (dbg)
-            fprintf(stderr, "[type numerics] %lld pairs: translate %.1f ms, host prep %.1f ms, gotoh %.1f ms (rows %.1f MB)\n", (long long)n, t_tr - t_0,
-                    t_prep - t_tr, now_ms() - t_prep, (double)row_total * 48 / 1e6);
+            fprintf(stderr, "[type numerics] %lld pairs (thread %lld, wide %lld + %lld + %lld, registers %lld + %lld): translate %.1f ms, host prep %.1f ms, gotoh %.1f ms\n",
+                    (long long)n, (long long)n_cls[0], (long long)n_cls[1], (long long)n_cls[2], (long long)n_cls[3], (long long)n_cls[4], (long long)n_cls[5], t_tr - t_0,
+                    t_prep - t_tr, now_ms() - t_prep);
         for (int64_t i = 0; i < n; ++i) {  // the n x 8 layout of kb_post_protein_align; coordinates are not produced here
             int32_t *o = res + i * 8;
             o[0] = r4[(size_t)i * 4], o[1] = r4[(size_t)i * 4 + 1], o[2] = r4[(size_t)i * 4 + 2], o[3] = r4[(size_t)i * 4 + 3];

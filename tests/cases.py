@@ -127,6 +127,23 @@ def case_big_indel():
     return db, _custom(2900, out, cuts=2)
 
 
+IS_GENES = (19, 28, 35)
+
+
+def case_is_insertion():
+    """Three genes each interrupted by a 2 kb insertion (an IS element inside a locus gene, a common Kaptive input).  minimap2 with its
+    default long-join (bw_long 20000) reports ONE hit per gene with a 2 kb deletion-side gap; mapping spec v1 has no long-join and reports
+    the two flanks as TWO hits.  The golden vectors pin that documented deviation so that it cannot change silently."""
+    db = small_db()
+    rng = np.random.default_rng(81)
+    out = []
+    for gi in IS_GENES:
+        g = _gene(db, gi)
+        cut = len(g) * 45 // 100
+        out.append(np.concatenate([g[:cut], synth.random_dna(rng, 2000, 0.5), g[cut:]]))
+    return db, _custom(3100, out)
+
+
 def case_tiny_contigs():
     db = small_db()
     rng = np.random.default_rng(80)
@@ -192,6 +209,7 @@ CASES = {
     "repeat_gene": case_repeat_gene,
     "mosaic_gene": case_mosaic_gene,
     "big_indel": case_big_indel,
+    "is_insertion": case_is_insertion,
     "tiny_contigs": case_tiny_contigs,
     "empty_assembly": case_empty_assembly,
     "no_locus": case_no_locus,

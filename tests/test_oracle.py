@@ -182,6 +182,24 @@ def test_zdrop_split_and_repeat_filter_are_exercised():
     assert len(g20) >= 1 and g20["matches"].max() == len(db.genes[20])  # still found end to end without the repeat seeds
 
 
+def test_is_interrupted_gene_is_reported_as_two_flanks():
+    """Pins a DOCUMENTED deviation of mapping spec v1 from minimap2: without long-join / RMQ re-chaining a gene
+    interrupted by a 2 kb insertion comes out as two hits, one per flank, where minimap2 (bw_long 20000) joins them into one hit with
+    a 2 kb gap.  The flanks meet at the insertion point on the gene and lie 2 kb apart on the contig."""
+    db, contigs = cases.case_is_insertion()
+    r = ol.OracleDB(*db.flat()).map(*cases.flat_contigs(contigs))
+    for gi in cases.IS_GENES:
+        h = np.sort(r["hits"][(r["hits"]["gene"] == gi) & (r["hits"]["is_primary"] == 1)], order="q_start")
+        cut = len(db.genes[gi]) * 45 // 100
+        flanks = h[(h["q_end"] - h["q_start"]) > 200]
+        assert len(flanks) == 2, (gi, h[["q_start", "q_end", "t_start", "t_end"]])
+        a, b = flanks
+        assert a["q_start"] == 0 and b["q_end"] == len(db.genes[gi]) and abs(int(a["q_end"]) - cut) <= 30 and abs(int(b["q_start"]) - cut) <= 30
+        assert a["t_ctg"] == b["t_ctg"] and a["strand"] == b["strand"]
+        gap = int(b["t_start"]) - int(a["t_end"]) if a["strand"] >= 0 else int(a["t_start"]) - int(b["t_end"])
+        assert 1940 <= gap <= 2060, gap
+
+
 # ------------------------------------------------------------------ golden vectors
 @pytest.mark.parametrize("name", list(cases.CASES))
 def test_oracle_reproduces_golden(name):

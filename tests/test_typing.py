@@ -117,3 +117,30 @@ def _trans_of(tdb, db):
     off = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int64)
     aa, ao, al = post.translate(np.frombuffer(b"".join(db.genes), np.uint8), off, lens, np.zeros(len(lens), np.int8), to_stop=False)
     return [aa[int(o) : int(o) + int(n)].tobytes() for o, n in zip(ao, al)]
+
+
+@pytest.mark.gpu
+def test_warp_gotoh_kernels_equal_the_thread_kernel(monkeypatch):
+    """The protein DP of type_many runs one warp per pair (row state in registers for narrow bands, in shared memory for the wide
+    bands of frameshifted hits); KAPTIVE_B200_GOTOH_WARP=0 sends every pair through the thread-per-pair kernel, which is the one the
+    reference-pinned tests above were first written against.  Same scores and counts, so the same identities and gene states."""
+    from kaptive_b200 import mapper, serotype, workload
+
+    db, ranges = synth.make_ko_db(k_loci=12, k_genes=14, k_core=2, seed=3)
+    wl = workload.make_device_workload(db, 40, 400_000, mean_contigs=5, seed=21, device="cuda:0", locus_ranges=ranges, indel=(0.0, 0.01))
+    gi = mapper.GeneIndex(db.genes)
+    batch = mapper.AssemblyBatch(wl.ascii.data_ptr(), wl.contig_off, wl.contig_len, wl.asm_contig_start, device=0)
+    res = gi.map(batch)
+    tdb = serotype.TypingDB.from_synth(db)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("KAPTIVE_B200_GOTOH_WARP", mode)
+        t = serotype.type_many(tdb, batch, res, threads=2)
+        out[mode] = ({k: np.array(v) for k, v in t.gene_hits.items()}, np.array(t.typeable), np.array(t.problems), np.array(t.best_locus))
+    a, b = out["0"], out["1"]
+    assert len(a[0]["gene"]) > 500
+    wide = np.abs(a[0]["t_end"] - a[0]["t_start"]).min() < 300  # truncated hits: wide bands
+    assert wide
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k], equal_nan=True) if a[0][k].dtype.kind == "f" else np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
