@@ -27,6 +27,13 @@ def import_reference(shim: str = "oracle"):
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
+    # a `rammappy` cached from the other shim directory (test_abi imports the product shim) would win over sys.path: drop it, and the
+    # reference modules that bound it at import time
+    stale = [m for m in sys.modules if (m == "rammappy" or m.startswith("rammappy.")) and
+             not str(getattr(sys.modules[m], "__file__", "") or "").startswith(str(shim_dir))]
+    if stale:
+        for m in stale + [m for m in sys.modules if m == "kaptive" or m.startswith("kaptive.")]:
+            sys.modules.pop(m, None)
     import kaptive  # noqa: F401
 
     return kaptive
