@@ -7,12 +7,14 @@ compute entry points raise.  The library is built in-tree by ``kaptive_b200/buil
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-SO_PATH = HERE / "_lib" / "libkaptive_b200.so"
+# KAPTIVE_B200_LIB: another build of the library (kernel experiments); the in-tree build otherwise
+SO_PATH = Path(os.environ["KAPTIVE_B200_LIB"]) if os.environ.get("KAPTIVE_B200_LIB") else HERE / "_lib" / "libkaptive_b200.so"
 
 KB_N_STAGES = 6
 STAGE_NAMES = ("scan", "sort", "chain", "align", "final", "total")

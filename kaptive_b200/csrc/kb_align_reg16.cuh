@@ -27,6 +27,12 @@
 #ifdef __CUDACC__
 
 #define KB_R16_RING_WORDS (2 * KB_RING_WORDS)  // one ring of kb_rows' size per job of the pair
+// stripe width of the last tile: rounded up to an even number of columns per lane, so that the row code exists in four widths instead of
+// eight (the copies share the instruction cache of an SM; the extra column of an odd width costs less than the misses)
+#ifndef KB_R16_EVEN
+#define KB_R16_EVEN 1
+#endif
+#define KB_R16_KACT(k) (KB_R16_EVEN ? (((k) + 1) & ~1) : (k))
 // per-warp shared memory of kb_rows16: the two rings, a 5-entry table of query score words per job, and the two query segments
 // as nt4 bytes in DP order with 32 bytes of padding on either side (a lane reads row s - lane for -31 <= s - lane < qlen + 31)
 #define KB_R16_QMAX 2048
@@ -177,6 +183,14 @@ __device__ __forceinline__ void kb_rows16_rowk(const KbC16 &c, int kact, uint32_
 {
 #define KB_RK(K) \
     kb_rows16_row<SLOW, TRACK, K>(c, qlo, qhi, sel, nbits, sNw, hu, e1, e2, hd, Hc, F1, F2, tb, ring_lo, ring_hi, tinv, nv_lo, nv_hi, w_lo, w_hi, d0)
+#if KB_R16_EVEN
+    switch (kact) {
+    case 8: KB_RK(8); break;
+    case 6: KB_RK(6); break;
+    case 4: KB_RK(4); break;
+    default: KB_RK(2); break;
+    }
+#else
     switch (kact) {
     case 8: KB_RK(8); break;
     case 7: KB_RK(7); break;
@@ -187,6 +201,7 @@ __device__ __forceinline__ void kb_rows16_rowk(const KbC16 &c, int kact, uint32_
     case 2: KB_RK(2); break;
     default: KB_RK(1); break;
     }
+#endif
 #undef KB_RK
 }
 
@@ -250,7 +265,7 @@ static __device__ __forceinline__ void kb_zdrop_scan(const KbDpConst &P, int lan
 __device__ __forceinline__ int kb_pair_kact(int tlenA, int tlenB, int tile)
 {
     const int tl = tlenA > tlenB ? tlenA : tlenB, ntile = (tl + 255) >> 8;
-    return tile + 1 < ntile ? 8 : (tl - ((ntile - 1) << 8) + 31) >> 5;
+    return tile + 1 < ntile ? 8 : KB_R16_KACT((tl - ((ntile - 1) << 8) + 31) >> 5);
 }
 KB_HD bool kb_rows16_pair_fits(const KbDpConst &P, int qlenA, int tlenA, int qlenB, int tlenB)
 {
@@ -346,7 +361,7 @@ static __device__ __noinline__ void kb_rows16_dp(const KbDpConst P, int lane, co
     };
     for (int tile = 0; tile < ntile; ++tile) {
         const bool spill = tile + 1 < ntile;  // then the tile is full width and its last column is lane 31's slot 7
-        const int kact = spill ? 8 : (tmax - ((ntile - 1) << 8) + 31) >> 5;
+        const int kact = spill ? 8 : KB_R16_KACT((tmax - ((ntile - 1) << 8) + 31) >> 5);
         const int T0 = tile << 8, t0 = T0 + lane * kact;  // slot m holds column t0 + m
         const bool onA = tile < ntA, onB = tile < ntB;      // a job whose target ends in an earlier tile sits this one out
         const uint32_t *ein = edge + (size_t)((tile & 1) ^ 1) * 3 * KB_DP_MAXLEN;
