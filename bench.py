@@ -361,7 +361,9 @@ def run_ours(a):
                     keep[len(body) - 1 - pad : len(body) - 1] = False
                 parts += [b">c%d\n" % (c - c0), body[keep].tobytes()]
             fasta.append(b"".join(parts))
-    ingest_threads = min(os.cpu_count() or 1, 32)
+    from kaptive_b200.parallel import host_threads
+
+    ingest_threads = host_threads()
     best = None
     for _ in range(2):
         t0 = time.perf_counter()

@@ -10,6 +10,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from .parallel import host_threads
+
 from . import _lib
 from ._lib import ptr
 
@@ -27,7 +29,7 @@ def ingest_fasta(files: list[bytes], threads: int | None = None, out: np.ndarray
     """``files[i]`` = the FASTA bytes of assembly i.  ``out`` may be a preallocated (e.g. pinned) uint8 buffer for the sequences."""
     L = _lib.load()
     n = len(files)
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or host_threads()
     bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
     ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if len(b) else None for b in bufs])
     lens = np.array([len(b) for b in bufs], dtype=np.int64)
@@ -80,7 +82,7 @@ def read_fasta_files(paths, threads: int | None = None) -> tuple[list[bytes], li
         with opener(p, mode="rb") as fh:
             return fh.read()
 
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or host_threads()
     with ThreadPoolExecutor(max(1, min(threads, len(jobs) or 1))) as pool:
         data = list(pool.map(read, jobs))
     return data, [j[2] for j in jobs]
@@ -109,7 +111,7 @@ def ingest_fasta_packed(files: list[bytes], threads: int | None = None, out: tup
     straight into ``out = (seq2, nmask)`` (e.g. pinned uint32 arrays, reused from call to call) or fresh arrays."""
     L = _lib.load()
     n = len(files)
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or host_threads()
     bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
     ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if len(b) else None for b in bufs])
     lens = np.array([len(b) for b in bufs], dtype=np.int64)

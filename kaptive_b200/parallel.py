@@ -47,3 +47,16 @@ def gather_hits(hits: dict[str, np.ndarray], asm_offset: int, dst: int = 0) -> d
     if out is None:
         return None
     return {k: np.concatenate([o[k] for o in out]) for k in local}
+
+
+def host_threads(cap: int = 32) -> int:
+    """Host threads one process should use: this rank's share of the cores it is allowed to run on (torchrun sets LOCAL_WORLD_SIZE;
+    eight ranks of one box that each start a thread per core only get in each other's way), at least 2, at most `cap`."""
+    import os
+
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(cap, max(2 if cores > 1 else 1, cores // ranks)))

@@ -22,6 +22,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from .parallel import host_threads
+
 from . import _lib
 from ._lib import ptr
 
@@ -178,7 +180,7 @@ class TypedBatch:
 def score_loci(db: TypingDB, hits: dict[str, np.ndarray], n_asm: int, min_gene_coverage: float = 0.20, threads: int | None = None):
     """core.py:157-207 for a batch: (best locus per assembly, its un-penalised score, final scores, completeness)."""
     L = _lib.load()
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or host_threads()
     n = len(hits["gene"])
     scores = np.zeros((n_asm, db.n_loci), np.float64)
     counts = np.zeros((n_asm, db.n_loci), np.float32)
@@ -196,7 +198,7 @@ def type_many(db: TypingDB, batch, res, max_other_genes: int = 1, min_completene
               min_gene_coverage: float = 0.20, partial_edge_tolerance: int = 5, threads: int | None = None) -> TypedBatch:
     """Type every assembly of ``batch`` (a :class:`kaptive_b200.mapper.AssemblyBatch`) from the hits ``res`` of mapping it."""
     L = _lib.load()
-    threads = threads or min(os.cpu_count() or 1, 32)
+    threads = threads or host_threads()
     n_asm = batch.n_asm
     h = res.hits
     best, best_score, _, _ = score_loci(db, h, n_asm, min_gene_coverage, threads)
