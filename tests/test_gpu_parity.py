@@ -440,3 +440,32 @@ def test_batched_census_equals_the_per_assembly_census(monkeypatch):
         got = results[name]
         assert np.array_equal(got[0], ref[0]), (name, got[0], ref[0])
         assert all(np.array_equal(got[1][k], ref[1][k]) for k in ref[1]) and np.array_equal(got[2], ref[2]), name
+
+
+def test_batched_census_with_only_some_assemblies_flagged(monkeypatch):
+    """Only assemblies with repeats need the census: the batched form groups runs of flagged assemblies (bridging gaps of up to four
+    unflagged ones, which are scanned but not evaluated) and must leave every other assembly at the floor."""
+    from kaptive_b200 import mapper, synth, workload
+
+    db = synth.make_db(n_loci=6, genes_per_locus=6, n_core=1, seed=5)
+    n = 16
+    rep = workload.make_device_workload(db, n, 200_000, mean_contigs=4, seed=91, device="cuda:0", repeats=14, repeat_seq=db.genes[3])
+    plain = workload.make_device_workload(db, n, 200_000, mean_contigs=4, seed=91, device="cuda:0")
+    flagged = {0, 1, 4, 5, 14}  # a run, a gap of two (bridged), a gap of eight (a new group)
+    asms = []
+    for a in range(n):
+        seq, off, ln = (rep if a in flagged else plain).host_assembly(a)
+        asms.append([seq[o : o + k].tobytes() for o, k in zip(off, ln)])
+    gi = mapper.GeneIndex(db.genes, device=0)
+    batch = mapper.AssemblyBatch.from_contigs(asms, device=0)
+    out = {}
+    for name, env in (("serial", {"KAPTIVE_B200_CENSUS_SERIAL": "1"}), ("batched", {})):
+        monkeypatch.delenv("KAPTIVE_B200_CENSUS_SERIAL", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = gi.map(batch)
+        out[name] = (np.array(r.mid_occ), {k: np.array(v) for k, v in r.hits.items()}, np.array(r.cigar))
+    a, b = out["serial"], out["batched"]
+    assert np.array_equal(a[0], b[0]), (a[0], b[0])
+    assert all(np.array_equal(a[1][k], b[1][k]) for k in a[1]) and np.array_equal(a[2], b[2])
+    assert len(a[1]["gene"]) > 0
