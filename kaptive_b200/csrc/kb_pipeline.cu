@@ -518,7 +518,12 @@ __global__ void __launch_bounds__(128, KB_BAND_MINB) kb_band_kernel(KbIndexView 
 
 // packed certified band pass over the gap fills: one warp per PAIR of jobs (neighbours of the length-sorted queue), persistent
 #ifndef KB_BAND16_MINB
-#define KB_BAND16_MINB 5
+#define KB_BAND16_MINB 6  // 80 registers, 24 warps per SM: align 343.8 / 343.1 / 340.2 ms per 2000 assemblies at 4 / 5 / 6 CTAs per SM
+#endif
+// a wider window is taken while 64 K * KB_B16_WIN_RULE <= 2 (qlen + tlen); measured flat for 1 .. 4 (336.5 - 337.6 ms align per 2000
+// assemblies), worse above (5: 343.5, 6: 352.2, 8: 368.5): the window pass is cheaper per cell than the rectangle even where it has more cells
+#ifndef KB_B16_WIN_RULE
+#define KB_B16_WIN_RULE 3
 #endif
 template <int K>
 __global__ void __launch_bounds__(128, KB_BAND16_MINB) kb_band16_kernel(KbIndexView ix, KbBatchView bt, KbJob *jobs, const int32_t *sorted, KbBandQueues BQ,
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(128, KB_BAND16_MINB) kb_band16_kernel(KbIndexV
                 if (K == 1 && kb_band16_geometry(ql, tl, 2, dlo, dhi) && score > kb_band_bound64(P, ql, tl, dlo, dhi)) k2 = 2;
                 else if (K <= 2 && kb_band16_geometry(ql, tl, 4, dlo, dhi) && score > kb_band_bound64(P, ql, tl, dlo, dhi)) k2 = 4;
                 // worth it only while the window stays well below the rectangle
-                if (k2 && 64 * k2 * 3 <= 2 * (ql + tl)) kb_band16_enqueue(BQ, counters, k2 == 2 ? 1 : 2, *J[w], jid[w]);
+                if (k2 && 64 * k2 * KB_B16_WIN_RULE <= 2 * (ql + tl)) kb_band16_enqueue(BQ, counters, k2 == 2 ? 1 : 2, *J[w], jid[w]);
                 else kb_rows_enqueue(Q, P, counters, *J[w], jid[w]);
             }
         }
